@@ -1,0 +1,477 @@
+// Dense prefill attention on 5th-gen tensor cores: TMA-fed tcgen05.mma with TMEM accumulators.
+// Replaces flash-attn 2 (mma.sync) for the new-token prefill of HF Qwen2 attention
+// (streamvln_eval.py:526; reached from stream_video_vln.py:340): per turn ~216 new tokens, at a
+// window start ~1.8-2k, against [pruned memory | window KV | new tokens] in the KV arena.
+//
+// One CTA = one 128-row M tile of one (sequence, kv head).  Rows are the flattened
+// (query token, head-in-GQA-group) pairs R = tq * g + hg, so the g query heads that share a KV
+// head reuse every K/V tile (GQA packing) and causal limits are monotone in R.
+//
+//   warps 0-3 : softmax.  Thread i of warp w owns TMEM lane 32w+i = tile row 32w+i, so row max /
+//               row sum need no shuffles.  Loads S with tcgen05.ld, writes P (bf16) to swizzled
+//               smem, rescales O in TMEM lazily (only when the running max grew by > 2^8).
+//   warp 4    : one elected thread issues tcgen05.mma: S = Q K^T (SS, K-major x K-major) into a
+//               double-buffered S in TMEM, and O += P V (SS, K-major x MN-major).
+//   warp 5    : one elected thread issues TMA loads of K and V tiles (128 keys x 128 dims, two
+//               64-column SWIZZLE_128B panels each) into 2-stage rings.
+// TMEM: S0 cols [0,128), S1 [128,256), O [256,384) of a 512-column allocation.
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+#include "svln_common.cuh"
+
+namespace svln {
+
+constexpr int PF_BM = 128;   // rows per CTA tile
+constexpr int PF_BN = 128;   // keys per KV tile
+constexpr int PF_HD = 128;   // head_dim
+constexpr int PF_PANEL = 128 * 128;            // bytes of one [128 rows][64 elem] SW128 panel
+constexpr int PF_TILE = 2 * PF_PANEL;          // 32 KB: a [128][128] bf16 tile = two panels
+constexpr int PF_THREADS = 192;
+constexpr int PF_MAX_SEQ = 64;
+
+// shared memory map (dynamic, 1024-aligned)
+constexpr int SM_Q = 0;
+constexpr int SM_K = SM_Q + PF_TILE;           // 2 stages
+constexpr int SM_V = SM_K + 2 * PF_TILE;       // 2 stages
+constexpr int SM_P = SM_V + 2 * PF_TILE;
+constexpr int SM_BAR = SM_P + PF_TILE;         // barriers + tmem pointer
+constexpr int PF_SMEM = SM_BAR + 256 + 1024;   // + alignment slack
+
+enum { BAR_K_FULL = 0, BAR_K_EMPTY = 2, BAR_V_FULL = 4, BAR_V_EMPTY = 6, BAR_S_FULL = 8, BAR_S_EMPTY = 10,
+       BAR_P_FULL = 12, BAR_PV_DONE = 13, BAR_COUNT = 14 };
+
+struct PrefillParams {
+    const __nv_bfloat16* q;   // [n_tok, Hq, 128]
+    __nv_bfloat16* out;       // [n_tok, Hq*128]
+    int n_q_head, n_kv_head, n_layer, layer, max_len;
+    int n_seq;
+    float scale_log2;
+    int32_t env[PF_MAX_SEQ], q_start[PF_MAX_SEQ], n_q[PF_MAX_SEQ], kv_len[PF_MAX_SEQ];
+    int32_t tile_start[PF_MAX_SEQ + 1];  // prefix sum of M tiles per sequence
+};
+
+// ---------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t s2u(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accum) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+          "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
+          "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
+          "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): SWIZZLE_128B, version 1.
+//   bits [0,14) start>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version=1 | [61,64) layout=2
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor), kind::f16, bf16 x bf16 -> f32, M=128, N=128
+__host__ __device__ constexpr uint32_t umma_idesc(int b_mn_major) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)b_mn_major << 16) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+}
+
+// byte offset of 16-byte chunk c (0..15) of row r inside a K-major [128][128] SW128 tile (two panels)
+__device__ __forceinline__ uint32_t kmajor_off(int r, int c) {
+    return (uint32_t)((c >> 3) * PF_PANEL + r * 128 + (((c & 7) ^ (r & 7)) << 4));
+}
+
+__global__ void __launch_bounds__(PF_THREADS, 1)
+attn_prefill_kernel(const __grid_constant__ CUtensorMap kv_map, const __grid_constant__ PrefillParams p) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const uint32_t sbase = s2u(smem);
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + SM_BAR + BAR_COUNT * 8);
+    const uint32_t bar0 = sbase + SM_BAR;
+    auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int kvh = blockIdx.y;
+    const int g = p.n_q_head / p.n_kv_head;
+
+    // locate (sequence, M tile)
+    int b = 0;
+    while (b + 1 < p.n_seq && (int)blockIdx.x >= p.tile_start[b + 1]) ++b;
+    const int mtile = blockIdx.x - p.tile_start[b];
+    const int nq = p.n_q[b], len = p.kv_len[b], env = p.env[b], qs = p.q_start[b];
+    const int rows_total = nq * g;
+    const int row0 = mtile * PF_BM;
+    const int rows_here = min(PF_BM, rows_total - row0);
+    const int tq_last = (row0 + rows_here - 1) / g;
+    const int kv_hi = len - nq + tq_last + 1;          // keys [0, kv_hi) are visible to some row
+    const int n_tiles = (kv_hi + PF_BN - 1) / PF_BN;
+    const int plane_k = ((env * p.n_layer + p.layer) * 2 + 0) * p.n_kv_head + kvh;
+    const int plane_v = plane_k + p.n_kv_head;
+
+    if (tid == 0) {
+        mbar_init(BAR(BAR_K_FULL), 1); mbar_init(BAR(BAR_K_FULL + 1), 1);
+        mbar_init(BAR(BAR_K_EMPTY), 1); mbar_init(BAR(BAR_K_EMPTY + 1), 1);
+        mbar_init(BAR(BAR_V_FULL), 1); mbar_init(BAR(BAR_V_FULL + 1), 1);
+        mbar_init(BAR(BAR_V_EMPTY), 1); mbar_init(BAR(BAR_V_EMPTY + 1), 1);
+        mbar_init(BAR(BAR_S_FULL), 1); mbar_init(BAR(BAR_S_FULL + 1), 1);
+        mbar_init(BAR(BAR_S_EMPTY), 128); mbar_init(BAR(BAR_S_EMPTY + 1), 128);
+        mbar_init(BAR(BAR_P_FULL), 128);
+        mbar_init(BAR(BAR_PV_DONE), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {  // TMEM allocation: 512 columns, by one full warp (which also frees it)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(s2u(tmem_ptr_smem)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    // Q tile -> swizzled smem (generic proxy), rows past the end are zero
+    if (tid < PF_BM) {
+        const int r = tid;
+        const int R = row0 + r;
+        int4 v[16];
+        if (r < rows_here) {
+            const int tq = R / g, hg = R - tq * g;
+            const int4* src = reinterpret_cast<const int4*>(p.q + ((int64_t)(qs + tq) * p.n_q_head + kvh * g + hg) * PF_HD);
+#pragma unroll
+            for (int c = 0; c < 16; ++c) v[c] = __ldg(src + c);
+        } else {
+#pragma unroll
+            for (int c = 0; c < 16; ++c) v[c] = make_int4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int c = 0; c < 16; ++c) *reinterpret_cast<int4*>(smem + SM_Q + kmajor_off(r, c)) = v[c];
+    }
+    fence_async_smem();  // make the generic-proxy smem writes visible to the async proxy (MMA)
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+    const uint32_t TM_S0 = tmem_base, TM_O = tmem_base + 256;
+
+    if (warp == 5) {
+        // ------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&kv_map) : "memory");
+            for (int j = 0; j < n_tiles; ++j) {
+                const int s = j & 1, u = j >> 1;
+                const int key0 = j * PF_BN;
+                mbar_wait(BAR(BAR_K_EMPTY + s), (u & 1) ^ 1);
+                mbar_expect_tx(BAR(BAR_K_FULL + s), PF_TILE);
+                tma_load_3d(sbase + SM_K + s * PF_TILE, &kv_map, BAR(BAR_K_FULL + s), 0, key0, plane_k);
+                tma_load_3d(sbase + SM_K + s * PF_TILE + PF_PANEL, &kv_map, BAR(BAR_K_FULL + s), 64, key0, plane_k);
+                mbar_wait(BAR(BAR_V_EMPTY + s), (u & 1) ^ 1);
+                mbar_expect_tx(BAR(BAR_V_FULL + s), PF_TILE);
+                tma_load_3d(sbase + SM_V + s * PF_TILE, &kv_map, BAR(BAR_V_FULL + s), 0, key0, plane_v);
+                tma_load_3d(sbase + SM_V + s * PF_TILE + PF_PANEL, &kv_map, BAR(BAR_V_FULL + s), 64, key0, plane_v);
+            }
+        }
+    } else if (warp == 4) {
+        // ------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            constexpr uint32_t IDESC_QK = umma_idesc(0);  // A, B K-major
+            constexpr uint32_t IDESC_PV = umma_idesc(1);  // B (V) MN-major
+            auto issue_qk = [&](int j) {
+                const int s = j & 1;
+                const uint32_t kb = sbase + SM_K + s * PF_TILE;
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks) {  // 16 dims per step; 4 steps per 64-dim panel
+                    const uint32_t off = (ks >> 2) * PF_PANEL + (ks & 3) * 32;
+                    tc_mma(TM_S0 + s * 128, umma_desc(sbase + SM_Q + off, 16, 1024), umma_desc(kb + off, 16, 1024),
+                           IDESC_QK, ks > 0);
+                }
+            };
+            mbar_wait(BAR(BAR_K_FULL), 0);
+            tc_fence_after();
+            issue_qk(0);
+            tc_commit(BAR(BAR_K_EMPTY));
+            tc_commit(BAR(BAR_S_FULL));
+            for (int j = 0; j < n_tiles; ++j) {
+                if (j + 1 < n_tiles) {  // S(j+1) overlaps softmax(j)
+                    const int s = (j + 1) & 1, u = (j + 1) >> 1;
+                    mbar_wait(BAR(BAR_K_FULL + s), u & 1);
+                    mbar_wait(BAR(BAR_S_EMPTY + s), (u & 1) ^ 1);
+                    tc_fence_after();
+                    issue_qk(j + 1);
+                    tc_commit(BAR(BAR_K_EMPTY + s));
+                    tc_commit(BAR(BAR_S_FULL + s));
+                }
+                const int s = j & 1, u = j >> 1;
+                mbar_wait(BAR(BAR_P_FULL), j & 1);
+                mbar_wait(BAR(BAR_V_FULL + s), u & 1);
+                tc_fence_after();
+                const uint32_t vb = sbase + SM_V + s * PF_TILE;
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks) {  // 16 keys per step
+                    // A = P: K-major (keys contiguous), 4 steps per 64-key panel
+                    const uint32_t aoff = (ks >> 2) * PF_PANEL + (ks & 3) * 32;
+                    // B = V: MN-major; 16 keys = two 8-row swizzle atoms = 2048 B; dims panels 16 KB apart
+                    tc_mma(TM_O, umma_desc(sbase + SM_P + aoff, 16, 1024), umma_desc(vb + ks * 2048, PF_PANEL, 1024),
+                           IDESC_PV, (j > 0 || ks > 0));
+                }
+                tc_commit(BAR(BAR_V_EMPTY + s));
+                tc_commit(BAR(BAR_PV_DONE));
+            }
+        }
+    } else {
+        // ------------------------------------------------------------ softmax warps (rows)
+        const int r = tid;                       // tile row == TMEM lane
+        const int R = row0 + r;
+        const bool row_valid = r < rows_here;
+        const int tq = row_valid ? R / g : 0;
+        const int hg = row_valid ? R - tq * g : 0;
+        const int lim = row_valid ? len - nq + tq + 1 : 0;   // keys < lim are visible
+        const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
+        float m_used = -INFINITY;   // running max in scaled (log2) units
+        float l_sum = 0.f;
+        for (int j = 0; j < n_tiles; ++j) {
+            const int s = j & 1, u = j >> 1;
+            mbar_wait(BAR(BAR_S_FULL + s), u & 1);
+            tc_fence_after();
+            uint32_t sv[4][32];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) tmem_ld32(TM_S0 + s * 128 + lane_addr + c * 32, sv[c]);
+            tmem_wait_ld();
+            tc_fence_before();
+            mbar_arrive(BAR(BAR_S_EMPTY + s));
+            // scale, mask, row max
+            const int key0 = j * PF_BN;
+            const bool need_mask = key0 + PF_BN > lim;
+            float mx = -INFINITY;
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+#pragma unroll
+                for (int e = 0; e < 32; ++e) {
+                    float x = __uint_as_float(sv[c][e]) * p.scale_log2;
+                    if (need_mask && key0 + c * 32 + e >= lim) x = -INFINITY;
+                    sv[c][e] = __float_as_uint(x);
+                    mx = fmaxf(mx, x);
+                }
+            // lazy rescale: only move the reference max when it grew by more than 8 (factor 256)
+            float alpha = 1.f;
+            bool rescale = false;
+            if (mx > m_used + 8.0f || (m_used == -INFINITY && mx != -INFINITY)) {
+                alpha = m_used == -INFINITY ? 0.f : exp2f(m_used - mx);
+                m_used = mx;
+                rescale = j > 0;
+            }
+            const float m_sub = m_used == -INFINITY ? 0.f : m_used;
+            // P buffer and O are free once PV(j-1) has completed
+            if (j > 0) mbar_wait(BAR(BAR_PV_DONE), (j - 1) & 1);
+            tc_fence_after();
+            if (__any_sync(0xffffffffu, rescale)) {
+                l_sum *= alpha;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t ov[32];
+                    tmem_ld32(TM_O + lane_addr + c * 32, ov);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) ov[e] = __float_as_uint(__uint_as_float(ov[e]) * alpha);
+                    tmem_st32(TM_O + lane_addr + c * 32, ov);
+                }
+                tmem_wait_st();
+            } else {
+                l_sum *= alpha;  // alpha == 1 unless this is the first tile
+            }
+            // P = exp2(S - m), row sum in fp32, P rounded to bf16 into swizzled smem
+            float psum = 0.f;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {  // 8 keys = one 16-byte chunk
+                    uint32_t w[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float p0 = exp2f(__uint_as_float(sv[c][q * 8 + 2 * e]) - m_sub);
+                        const float p1 = exp2f(__uint_as_float(sv[c][q * 8 + 2 * e + 1]) - m_sub);
+                        psum += p0 + p1;
+                        w[e] = f32_to_bf16_bits(p0) | (f32_to_bf16_bits(p1) << 16);
+                    }
+                    *reinterpret_cast<int4*>(smem + SM_P + kmajor_off(r, c * 4 + q)) = make_int4(w[0], w[1], w[2], w[3]);
+                }
+            }
+            l_sum += psum;
+            fence_async_smem();
+            tc_fence_before();
+            mbar_arrive(BAR(BAR_P_FULL));
+        }
+        // epilogue: O / l -> bf16 -> global
+        mbar_wait(BAR(BAR_PV_DONE), (n_tiles - 1) & 1);
+        tc_fence_after();
+        const float inv_l = l_sum > 0.f ? 1.0f / l_sum : 0.f;
+        __nv_bfloat16* orow = p.out + ((int64_t)(qs + tq) * p.n_q_head + kvh * g + hg) * PF_HD;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            uint32_t ov[32];
+            tmem_ld32(TM_O + lane_addr + c * 32, ov);
+            tmem_wait_ld();
+            if (row_valid) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    uint32_t w[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        w[e] = f32_to_bf16_bits(__uint_as_float(ov[q * 8 + 2 * e]) * inv_l) |
+                               (f32_to_bf16_bits(__uint_as_float(ov[q * 8 + 2 * e + 1]) * inv_l) << 16);
+                    *reinterpret_cast<int4*>(orow + c * 32 + q * 8) = make_int4(w[0], w[1], w[2], w[3]);
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------ host side
+struct MapCacheEntry {
+    void* base; int n_env, n_layer, n_kv_head, max_len; CUtensorMap map; bool valid;
+};
+static MapCacheEntry g_map_cache[8];
+
+static int get_kv_map(const svln_kv_arena* a, CUtensorMap* out) {
+    for (auto& e : g_map_cache)
+        if (e.valid && e.base == a->base && e.n_env == a->n_env && e.n_layer == a->n_layer &&
+            e.n_kv_head == a->n_kv_head && e.max_len == a->max_len) {
+            *out = e.map;
+            return SVLN_OK;
+        }
+    static PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        SVLN_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        SVLN_REQUIRE(fn && qres == cudaDriverEntryPointSuccess, SVLN_ERR_CUDA, "cuTensorMapEncodeTiled not available");
+        encode = (PFN_cuTensorMapEncodeTiled_v12000)fn;
+    }
+    const cuuint64_t planes = (cuuint64_t)a->n_env * a->n_layer * 2 * a->n_kv_head;
+    cuuint64_t gdim[3] = {(cuuint64_t)PF_HD, (cuuint64_t)a->max_len, planes};
+    cuuint64_t gstride[2] = {(cuuint64_t)PF_HD * 2, (cuuint64_t)a->max_len * PF_HD * 2};
+    cuuint32_t box[3] = {64, (cuuint32_t)PF_BN, 1};
+    cuuint32_t estride[3] = {1, 1, 1};
+    CUtensorMap m;
+    CUresult r = encode(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, a->base, gdim, gstride, box, estride,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    SVLN_REQUIRE(r == CUDA_SUCCESS, SVLN_ERR_CUDA, "cuTensorMapEncodeTiled failed with %d", (int)r);
+    static int next = 0;
+    MapCacheEntry& e = g_map_cache[next++ % 8];
+    e = {a->base, a->n_env, a->n_layer, a->n_kv_head, a->max_len, m, true};
+    *out = m;
+    return SVLN_OK;
+}
+
+}  // namespace svln
+
+using namespace svln;
+
+extern "C" {
+
+int svln_attn_prefill(const svln_kv_arena* arena, int layer, const void* q, int n_q_head,
+                      const int32_t* seq_env_host, const int32_t* q_start_host, const int32_t* n_q_host,
+                      const int32_t* kv_len_host, int n_seq, float scale, void* workspace, size_t workspace_bytes,
+                      void* out, svln_stream_t stream) {
+    (void)workspace; (void)workspace_bytes;
+    SVLN_REQUIRE(arena && arena->base && arena->head_dim == 128, SVLN_ERR_INVALID, "svln_attn_prefill: bad arena");
+    SVLN_REQUIRE(layer >= 0 && layer < arena->n_layer, SVLN_ERR_INVALID, "svln_attn_prefill: layer out of range");
+    SVLN_REQUIRE(n_q_head > 0 && n_q_head % arena->n_kv_head == 0, SVLN_ERR_INVALID,
+                 "svln_attn_prefill: n_q_head %d not a multiple of n_kv_head %d", n_q_head, arena->n_kv_head);
+    SVLN_REQUIRE(n_seq >= 0, SVLN_ERR_INVALID, "svln_attn_prefill: negative n_seq");
+    if (n_seq == 0) return SVLN_OK;
+    SVLN_REQUIRE(q && out && seq_env_host && q_start_host && n_q_host && kv_len_host, SVLN_ERR_INVALID,
+                 "svln_attn_prefill: null pointer");
+    SVLN_REQUIRE(((uintptr_t)arena->base & 1023) == 0, SVLN_ERR_INVALID, "svln_attn_prefill: arena base must be 1024-byte aligned");
+    CUtensorMap map;
+    int rc = get_kv_map(arena, &map);
+    if (rc) return rc;
+    static bool attr_set = false;
+    if (!attr_set) {
+        SVLN_CUDA(cudaFuncSetAttribute(attn_prefill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PF_SMEM));
+        attr_set = true;
+    }
+    const int g = n_q_head / arena->n_kv_head;
+    for (int s0 = 0; s0 < n_seq; s0 += PF_MAX_SEQ) {
+        PrefillParams p;
+        p.q = (const __nv_bfloat16*)q;
+        p.out = (__nv_bfloat16*)out;
+        p.n_q_head = n_q_head; p.n_kv_head = arena->n_kv_head; p.n_layer = arena->n_layer; p.layer = layer;
+        p.max_len = arena->max_len;
+        p.scale_log2 = scale * 1.4426950408889634f;
+        const int ns = n_seq - s0 < PF_MAX_SEQ ? n_seq - s0 : PF_MAX_SEQ;
+        p.n_seq = ns;
+        int tiles = 0;
+        for (int i = 0; i < ns; ++i) {
+            const int b = s0 + i;
+            SVLN_REQUIRE(seq_env_host[b] >= 0 && seq_env_host[b] < arena->n_env, SVLN_ERR_INVALID,
+                         "svln_attn_prefill: env %d out of range", seq_env_host[b]);
+            SVLN_REQUIRE(n_q_host[b] >= 1 && kv_len_host[b] >= n_q_host[b] && kv_len_host[b] <= arena->max_len,
+                         SVLN_ERR_INVALID, "svln_attn_prefill: bad lengths n_q=%d kv_len=%d", n_q_host[b], kv_len_host[b]);
+            p.env[i] = seq_env_host[b]; p.q_start[i] = q_start_host[b]; p.n_q[i] = n_q_host[b]; p.kv_len[i] = kv_len_host[b];
+            p.tile_start[i] = tiles;
+            tiles += (n_q_host[b] * g + PF_BM - 1) / PF_BM;
+        }
+        p.tile_start[ns] = tiles;
+        for (int i = ns + 1; i <= PF_MAX_SEQ; ++i) p.tile_start[i] = tiles;
+        dim3 grid(tiles, arena->n_kv_head);
+        attn_prefill_kernel<<<grid, PF_THREADS, PF_SMEM, (cudaStream_t)stream>>>(map, p);
+        rc = check_launch("attn_prefill_kernel");
+        if (rc) return rc;
+    }
+    return SVLN_OK;
+}
+
+}  // extern "C"

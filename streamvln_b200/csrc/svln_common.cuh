@@ -1,0 +1,78 @@
+// Shared helpers for libsvln (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/svln.h"
+
+namespace svln {
+
+void set_error(const char* fmt, ...);
+int check_launch(const char* what);
+int sm_count();
+
+#define SVLN_REQUIRE(cond, code, ...)      \
+    do {                                   \
+        if (!(cond)) {                     \
+            svln::set_error(__VA_ARGS__);  \
+            return (code);                 \
+        }                                  \
+    } while (0)
+
+#define SVLN_CUDA(call)                                                              \
+    do {                                                                             \
+        cudaError_t e__ = (call);                                                    \
+        if (e__ != cudaSuccess) {                                                    \
+            svln::set_error("%s failed: %s", #call, cudaGetErrorString(e__));        \
+            return SVLN_ERR_CUDA;                                                    \
+        }                                                                            \
+    } while (0)
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// 128-bit streaming loads/stores that do not pollute L1 (rows are touched once).
+__device__ __forceinline__ int4 ld_stream(const int4* p) {
+    int4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void st_stream(int4* p, const int4& v) {
+    asm volatile("st.global.L1::no_allocate.v4.s32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x),
+                 "r"(v.y), "r"(v.z), "r"(v.w));
+}
+// plain (coherent) 128-bit load for data written earlier by other CTAs of the same kernel
+__device__ __forceinline__ int4 ld_cg(const int4* p) {
+    int4 r;
+    asm volatile("ld.global.cg.v4.s32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+
+__device__ __forceinline__ float bf16_bits_to_f32(uint32_t b16) {
+    return __uint_as_float(b16 << 16);
+}
+// round-to-nearest-even fp32 -> bf16 bits (matches torch / numpy-ml_dtypes rounding, NaN kept)
+__device__ __forceinline__ uint32_t f32_to_bf16_bits(float f) {
+    return (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(f));
+}
+__device__ __forceinline__ float round_bf16(float f) {
+    return bf16_bits_to_f32(f32_to_bf16_bits(f));
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+}  // namespace svln
