@@ -434,7 +434,7 @@ int svln_attn_prefill(const svln_kv_arena* arena, int layer, const void* q, int 
     if (n_seq == 0) return SVLN_OK;
     SVLN_REQUIRE(q && out && seq_env_host && q_start_host && n_q_host && kv_len_host, SVLN_ERR_INVALID,
                  "svln_attn_prefill: null pointer");
-    SVLN_REQUIRE(((uintptr_t)arena->base & 1023) == 0, SVLN_ERR_INVALID, "svln_attn_prefill: arena base must be 1024-byte aligned");
+    SVLN_REQUIRE(((uintptr_t)arena->base & 15) == 0, SVLN_ERR_INVALID, "svln_attn_prefill: arena base must be 16-byte aligned");
     CUtensorMap map;
     int rc = get_kv_map(arena, &map);
     if (rc) return rc;

@@ -1,0 +1,377 @@
+"""Qwen2 decoder driven by libsvln kernels — the LLM arithmetic behind `generate`.
+
+Replaces HF `Qwen2ForCausalLM.forward` + `DynamicCache` + flash-attn 2 as reached from
+streamvln/model/stream_video_vln.py:340,402.  The linears (QKV, O, gate/up, down, lm_head) stay
+cuBLAS through torch ("linears stay torch/cuBLAS"); everything between them is
+hand-written sm_100a CUDA behind the C-ABI: RMSNorm(+residual), fused RoPE + KV append, tcgen05
+prefill attention, split-KV decode attention, SwiGLU, argmax.  Tokens of several streams (envs) are
+packed into one [n_tok, hidden] batch so every GEMM serves all concurrent episodes.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence
+
+import torch
+import torch.nn.functional as F
+
+from . import _lib
+from ._lib import check, cur_stream, ptr
+from .kv_arena import KvArena
+
+
+@dataclass
+class Qwen2Config:
+    hidden_size: int = 3584
+    num_hidden_layers: int = 28
+    num_attention_heads: int = 28
+    num_key_value_heads: int = 4
+    head_dim: int = 128
+    intermediate_size: int = 18944
+    vocab_size: int = 152064
+    rope_theta: float = 1e6
+    rms_norm_eps: float = 1e-6
+    max_position_embeddings: int = 4096  # arena rows per stream (reference: model_max_length 4096)
+
+    @staticmethod
+    def qwen2_7b() -> "Qwen2Config":
+        return Qwen2Config()
+
+    @staticmethod
+    def tiny(vocab_size: int = 512, layers: int = 2, max_pos: int = 1024) -> "Qwen2Config":
+        return Qwen2Config(hidden_size=256, num_hidden_layers=layers, num_attention_heads=4,
+                           num_key_value_heads=2, head_dim=128, intermediate_size=512, vocab_size=vocab_size,
+                           max_position_embeddings=max_pos)
+
+
+class Qwen2Weights:
+    """bf16 weights on the device, QKV and gate/up fused row-wise (same dot products as HF, fewer GEMMs).
+    Names follow HF `Qwen2ForCausalLM` state dicts (`model.layers.N.self_attn.q_proj.weight`, ...)."""
+
+    def __init__(self, cfg: Qwen2Config, device):
+        self.cfg, self.device = cfg, torch.device(device)
+        self.embed: torch.Tensor = None
+        self.lm_head: torch.Tensor = None
+        self.final_norm: torch.Tensor = None
+        self.layers: List[Dict[str, torch.Tensor]] = []
+
+    @staticmethod
+    def random(cfg: Qwen2Config, device, seed: int = 0, std: float = 0.02, lm_head_std: Optional[float] = None) -> "Qwen2Weights":
+        """Random init N(0, std) (HF initializer_range 0.02), generated on the device.  lm_head_std lets
+        tests spread the logits so that greedy argmax is not a coin flip between near-ties."""
+        w = Qwen2Weights(cfg, device)
+        g = torch.Generator(device=w.device).manual_seed(seed)
+        D, H, KV, hd, I = cfg.hidden_size, cfg.num_attention_heads, cfg.num_key_value_heads, cfg.head_dim, cfg.intermediate_size
+
+        def rnd(*shape, s=std):
+            return (torch.randn(*shape, generator=g, device=w.device, dtype=torch.float32) * s).to(torch.bfloat16)
+
+        w.embed = rnd(cfg.vocab_size, D)
+        w.lm_head = rnd(cfg.vocab_size, D, s=lm_head_std or std)
+        w.final_norm = torch.ones(D, dtype=torch.bfloat16, device=w.device)
+        for _ in range(cfg.num_hidden_layers):
+            w.layers.append(dict(
+                ln1=torch.ones(D, dtype=torch.bfloat16, device=w.device),
+                ln2=torch.ones(D, dtype=torch.bfloat16, device=w.device),
+                wqkv=rnd((H + 2 * KV) * hd, D), bqkv=rnd((H + 2 * KV) * hd),
+                wo=rnd(D, H * hd), wgu=rnd(2 * I, D), wd=rnd(D, I)))
+        return w
+
+    @staticmethod
+    def from_state_dict(cfg: Qwen2Config, sd: Dict[str, torch.Tensor], device) -> "Qwen2Weights":
+        w = Qwen2Weights(cfg, device)
+
+        def t(name):
+            return sd[name].to(device=w.device, dtype=torch.bfloat16).contiguous()
+
+        w.embed = t("model.embed_tokens.weight")
+        w.lm_head = t("lm_head.weight") if "lm_head.weight" in sd else w.embed
+        w.final_norm = t("model.norm.weight")
+        for i in range(cfg.num_hidden_layers):
+            p = f"model.layers.{i}."
+            w.layers.append(dict(
+                ln1=t(p + "input_layernorm.weight"), ln2=t(p + "post_attention_layernorm.weight"),
+                wqkv=torch.cat([t(p + "self_attn.q_proj.weight"), t(p + "self_attn.k_proj.weight"),
+                                t(p + "self_attn.v_proj.weight")]).contiguous(),
+                bqkv=torch.cat([t(p + "self_attn.q_proj.bias"), t(p + "self_attn.k_proj.bias"),
+                                t(p + "self_attn.v_proj.bias")]).contiguous(),
+                wo=t(p + "self_attn.o_proj.weight"),
+                wgu=torch.cat([t(p + "mlp.gate_proj.weight"), t(p + "mlp.up_proj.weight")]).contiguous(),
+                wd=t(p + "mlp.down_proj.weight")))
+        return w
+
+    def to_hf_state_dict(self) -> Dict[str, torch.Tensor]:
+        """Un-fuse into HF Qwen2ForCausalLM names (used by the CPU oracle to load identical weights)."""
+        cfg = self.cfg
+        H, KV, hd, I = cfg.num_attention_heads, cfg.num_key_value_heads, cfg.head_dim, cfg.intermediate_size
+        sd = {"model.embed_tokens.weight": self.embed, "lm_head.weight": self.lm_head, "model.norm.weight": self.final_norm}
+        for i, L in enumerate(self.layers):
+            p = f"model.layers.{i}."
+            q, k, v = L["wqkv"].split([H * hd, KV * hd, KV * hd])
+            bq, bk, bv = L["bqkv"].split([H * hd, KV * hd, KV * hd])
+            gate, up = L["wgu"].split([I, I])
+            sd.update({p + "input_layernorm.weight": L["ln1"], p + "post_attention_layernorm.weight": L["ln2"],
+                       p + "self_attn.q_proj.weight": q, p + "self_attn.k_proj.weight": k, p + "self_attn.v_proj.weight": v,
+                       p + "self_attn.q_proj.bias": bq, p + "self_attn.k_proj.bias": bk, p + "self_attn.v_proj.bias": bv,
+                       p + "self_attn.o_proj.weight": L["wo"], p + "mlp.gate_proj.weight": gate,
+                       p + "mlp.up_proj.weight": up, p + "mlp.down_proj.weight": L["wd"]})
+        return {k: v.detach().cpu() for k, v in sd.items()}
+
+
+@dataclass
+class Chunk:
+    """New tokens of one stream in a packed forward: rows [q_start, q_start+n_q) of the batch."""
+    env: int
+    q_start: int
+    n_q: int
+    kv_len: int  # cache length of the stream AFTER these tokens are appended
+
+
+class Qwen2Engine:
+    # chunks of at most this many tokens use the split-KV decode kernel; longer ones the tcgen05 prefill
+    DECODE_MAX_NQ = 2
+
+    def __init__(self, cfg: Qwen2Config, weights: Qwen2Weights, n_env: int = 1, device="cuda"):
+        self.lib = _lib.load()
+        self.cfg, self.w = cfg, weights
+        self.device = torch.device(device)
+        self.arena = KvArena(n_env, cfg.num_hidden_layers, cfg.num_key_value_heads, cfg.head_dim,
+                             cfg.max_position_embeddings, cfg.rope_theta, self.device)
+        self.scale = cfg.head_dim ** -0.5
+        self.launches = 0  # libsvln kernel launches (bench.py reports them as gpu_launches)
+        self._graphs: Dict[int, "_DecodeGraph"] = {}
+
+    # ------------------------------------------------------------------ small kernels
+    def _rmsnorm(self, x: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
+        out = torch.empty_like(x)
+        check(self.lib.svln_rmsnorm(ptr(x), ptr(w), x.shape[0], x.shape[1], self.cfg.rms_norm_eps, ptr(out), cur_stream()))
+        self.launches += 1
+        return out
+
+    def _add_rmsnorm(self, x: torch.Tensor, r: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
+        out = torch.empty_like(x)
+        check(self.lib.svln_add_rmsnorm(ptr(x), ptr(r), ptr(w), x.shape[0], x.shape[1], self.cfg.rms_norm_eps, ptr(out),
+                                        cur_stream()))
+        self.launches += 1
+        return out
+
+    def _swiglu(self, gu: torch.Tensor) -> torch.Tensor:
+        inter = gu.shape[1] // 2
+        out = torch.empty(gu.shape[0], inter, dtype=gu.dtype, device=gu.device)
+        check(self.lib.svln_swiglu(ptr(gu), gu.shape[0], inter, ptr(out), cur_stream()))
+        self.launches += 1
+        return out
+
+    def argmax(self, logits: torch.Tensor) -> torch.Tensor:
+        out = torch.empty(logits.shape[0], dtype=torch.int64, device=logits.device)
+        check(self.lib.svln_argmax(ptr(logits), 1 if logits.dtype == torch.float32 else 0, logits.shape[0],
+                                   logits.shape[1], ptr(out), cur_stream()))
+        self.launches += 1
+        return out
+
+    # ------------------------------------------------------------------ layer stack
+    def _layers(self, h: torch.Tensor, tok_env: torch.Tensor, tok_pos: torch.Tensor, attn) -> torch.Tensor:
+        """h [n_tok, D] bf16 (modified in place as the residual stream).  attn(layer, q, out) runs the
+        attention kernel for this packed batch.  Returns the residual stream after the last layer with the
+        last MLP output still pending in `pending` form: (h, r) -> caller applies final add+norm."""
+        cfg = self.cfg
+        H = cfg.num_attention_heads
+        n_tok = h.shape[0]
+        q_rot = torch.empty(n_tok, H, cfg.head_dim, dtype=torch.bfloat16, device=h.device)
+        attn_out = torch.empty(n_tok, H * cfg.head_dim, dtype=torch.bfloat16, device=h.device)
+        pending = None  # MLP output of the previous layer, added to h by the next fused add+norm
+        for li, L in enumerate(self.w.layers):
+            x = self._rmsnorm(h, L["ln1"]) if pending is None else self._add_rmsnorm(h, pending, L["ln1"])
+            qkv = torch.addmm(L["bqkv"], x, L["wqkv"].t())
+            self.arena.append_rope(li, qkv, H, tok_env, tok_pos, q_rot)
+            self.launches += 1
+            attn(li, q_rot, attn_out)
+            o = attn_out @ L["wo"].t()
+            x = self._add_rmsnorm(h, o, L["ln2"])
+            pending = self._swiglu(x @ L["wgu"].t()) @ L["wd"].t()
+        return h, pending
+
+    def forward(self, h: torch.Tensor, chunks: Sequence[Chunk], last_only: bool = True) -> torch.Tensor:
+        """Packed forward of new tokens for several streams.  h [n_tok, D] bf16 input embeddings (consumed).
+        Appends K/V to the arena, returns fp32 logits [n_chunks, vocab] of each chunk's last token (the
+        reference computes lm_head for every prefill row and discards all but the last)."""
+        dev = h.device
+        n_tok = h.shape[0]
+        envs, poss = [], []
+        for c in chunks:
+            envs += [c.env] * c.n_q
+            poss += list(range(c.kv_len - c.n_q, c.kv_len))
+            if c.kv_len > self.arena.max_len:
+                raise ValueError(f"stream {c.env}: {c.kv_len} tokens exceed the arena ({self.arena.max_len} rows)")
+        assert len(envs) == n_tok
+        meta = torch.tensor([envs, poss], dtype=torch.int32).to(dev, non_blocking=True)
+        tok_env, tok_pos = meta[0], meta[1]
+        max_nq = max(c.n_q for c in chunks)
+        if max_nq <= self.DECODE_MAX_NQ:
+            d = torch.tensor([[c.env for c in chunks], [c.q_start for c in chunks], [c.n_q for c in chunks],
+                              [c.kv_len for c in chunks]], dtype=torch.int32).to(dev, non_blocking=True)
+            max_kv = max(c.kv_len for c in chunks)
+
+            def attn(li, q, out):
+                self.arena.attn_decode(li, q, self.cfg.num_attention_heads, d[0], d[1], d[2], d[3], max_nq, max_kv,
+                                       self.scale, out)
+                self.launches += 2
+        else:
+            se, qs = [c.env for c in chunks], [c.q_start for c in chunks]
+            nq, kl = [c.n_q for c in chunks], [c.kv_len for c in chunks]
+
+            def attn(li, q, out):
+                self.arena.attn_prefill(li, q, self.cfg.num_attention_heads, se, qs, nq, kl, self.scale, out)
+                self.launches += 1
+        h, pending = self._layers(h, tok_env, tok_pos, attn)
+        for c in chunks:
+            self.arena.lens[c.env] = c.kv_len
+        if last_only:
+            rows = torch.tensor([c.q_start + c.n_q - 1 for c in chunks], dtype=torch.int64).to(dev, non_blocking=True)
+            h, pending = h.index_select(0, rows), pending.index_select(0, rows)
+        x = self._add_rmsnorm(h, pending, self.w.final_norm)
+        return (x @ self.w.lm_head.t()).float()
+
+    # ------------------------------------------------------------------ greedy generation
+    @torch.no_grad()
+    def generate(self, embeds: Sequence[torch.Tensor], envs: Sequence[int], max_new_tokens: int,
+                 eos_token_id: Optional[int] = None, use_graph: bool = True) -> List[torch.Tensor]:
+        """Greedy decoding for a batch of streams (HF `GenerationMixin._sample`, do_sample=False, as called at
+        streamvln/streamvln_agent.py:244).  embeds[i] [n_i, D] = un-cached tail of stream envs[i] (its cache
+        already holds arena.lens[env] rows).  Returns new token ids per stream ([n_gen_i] int64, device).
+        The last generated token is not fed back, so the cache grows by n_i + n_gen_i - 1."""
+        B = len(envs)
+        chunks, q0 = [], 0
+        for e, env in zip(embeds, envs):
+            chunks.append(Chunk(env, q0, e.shape[0], self.arena.lens[env] + e.shape[0]))
+            q0 += e.shape[0]
+        h = torch.cat(list(embeds), dim=0) if B > 1 else embeds[0].clone()
+        logits = self.forward(h, chunks)
+        tok = self.argmax(logits)
+        out = [tok]
+        if max_new_tokens > 1:
+            runner = self._decode_runner(envs, use_graph)
+            alive = None
+            for _ in range(max_new_tokens - 1):
+                if eos_token_id is not None:
+                    done = tok == eos_token_id
+                    alive = ~done if alive is None else alive & ~done
+                    if not bool(alive.any()):
+                        break
+                tok = runner.step(tok)
+                out.append(tok)
+            runner.finish()
+        seqs = torch.stack(out, dim=1)  # [B, n_steps]
+        res = []
+        for b in range(B):
+            s = seqs[b]
+            if eos_token_id is not None:
+                hit = (s == eos_token_id).nonzero()
+                if hit.numel():
+                    n = int(hit[0]) + 1
+                    s = s[:n]
+                    # tokens fed after this stream's EOS were appended to its cache: roll the length back
+                    self.arena.lens[envs[b]] -= (seqs.shape[1] - n)
+            res.append(s)
+        return res
+
+    def _decode_runner(self, envs: Sequence[int], use_graph: bool) -> "_DecodeRunner":
+        return _DecodeRunner(self, list(envs), use_graph)
+
+    def decode_step(self, tok: torch.Tensor, state: "_DecodeState") -> torch.Tensor:
+        """One packed decode step: every stream feeds one token.  All descriptors are device tensors, so
+        this sequence of launches is CUDA-graph capturable."""
+        cfg = self.cfg
+        state.kv_len.add_(1)
+        torch.sub(state.kv_len, 1, out=state.tok_pos)
+        h = self.w.embed.index_select(0, tok)
+        H = cfg.num_attention_heads
+
+        def attn(li, q, out):
+            self.arena.attn_decode(li, q, H, state.seq_env, state.q_start, state.n_q, state.kv_len, 1, state.max_kv,
+                                   self.scale, out)
+            self.launches += 2
+        h, pending = self._layers(h, state.seq_env, state.tok_pos, attn)
+        x = self._add_rmsnorm(h, pending, self.w.final_norm)
+        logits = (x @ self.w.lm_head.t()).float()
+        return self.argmax(logits)
+
+
+class _DecodeState:
+    def __init__(self, eng: Qwen2Engine, envs: List[int]):
+        dev = eng.device
+        B = len(envs)
+        self.seq_env = torch.tensor(envs, dtype=torch.int32, device=dev)
+        self.q_start = torch.arange(B, dtype=torch.int32, device=dev)
+        self.n_q = torch.ones(B, dtype=torch.int32, device=dev)
+        self.kv_len = torch.tensor([eng.arena.lens[e] for e in envs], dtype=torch.int32, device=dev)
+        self.tok_pos = torch.empty(B, dtype=torch.int32, device=dev)
+        self.max_kv = eng.arena.max_len
+
+
+class _DecodeRunner:
+    """Runs packed decode steps, replaying a CUDA graph captured once per batch size (the launch-bound
+    inner loop: ~12 launches per layer per token)."""
+
+    def __init__(self, eng: Qwen2Engine, envs: List[int], use_graph: bool):
+        self.eng, self.envs, self.steps = eng, envs, 0
+        B = len(envs)
+        self.graph = None
+        if use_graph:
+            g = eng._graphs.get(B)
+            if g is None:
+                g = _DecodeGraph(eng, B)
+                eng._graphs[B] = g
+            self.graph = g
+            g.bind(envs)
+        else:
+            self.state = _DecodeState(eng, envs)
+
+    def step(self, tok: torch.Tensor) -> torch.Tensor:
+        self.steps += 1
+        for e in self.envs:
+            if self.eng.arena.lens[e] + self.steps > self.eng.arena.max_len:
+                raise ValueError(f"stream {e}: decode exceeds the arena ({self.eng.arena.max_len} rows)")
+        if self.graph is not None:
+            return self.graph.replay(tok)
+        return self.eng.decode_step(tok, self.state)
+
+    def finish(self) -> None:
+        for e in self.envs:
+            self.eng.arena.lens[e] += self.steps
+
+
+class _DecodeGraph:
+    def __init__(self, eng: Qwen2Engine, B: int):
+        self.eng = eng
+        self.state = _DecodeState(eng, [0] * B)
+        self.tok_in = torch.zeros(B, dtype=torch.int64, device=eng.device)
+        self.launches_per_replay = 0
+        # warm up on a side stream (allocator, cuBLAS workspaces), then capture.  Capture appends garbage
+        # rows past each stream's current length, which later real appends overwrite.
+        saved = [eng.arena.lens[0]]
+        self.state.kv_len.fill_(0)
+        s = torch.cuda.Stream(device=eng.device)
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            eng.decode_step(self.tok_in, self.state)
+        torch.cuda.current_stream().wait_stream(s)
+        self.state.kv_len.fill_(0)
+        before = eng.launches
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.tok_out = eng.decode_step(self.tok_in, self.state)
+        self.launches_per_replay = eng.launches - before
+        eng.launches = before
+        eng.arena.lens[0] = saved[0]
+
+    def bind(self, envs: List[int]) -> None:
+        eng = self.eng
+        self.state.seq_env.copy_(torch.tensor(envs, dtype=torch.int32), non_blocking=True)
+        self.state.kv_len.copy_(torch.tensor([eng.arena.lens[e] for e in envs], dtype=torch.int32), non_blocking=True)
+
+    def replay(self, tok: torch.Tensor) -> torch.Tensor:
+        self.tok_in.copy_(tok)
+        self.graph.replay()
+        self.eng.launches += self.launches_per_replay
+        return self.tok_out.clone()
