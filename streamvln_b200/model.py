@@ -1,0 +1,280 @@
+"""`StreamVLNForCausalLM`-compatible model object over the B200 kernels.
+
+Drop-in for streamvln/model/stream_video_vln.py at its three call sites (streamvln_agent.py:244,
+streamvln_eval.py:332, streamvln_dagger.py:307): `generate(**kw)` with the same kwargs, returning an
+object with `.sequences` (new token ids only) and `.past_key_values` (opaque handle); `reset(env_num)`,
+`reset_for_env(env_idx)`; `.model.num_history`; `.get_vision_tower().image_processor`; `.eval()`,
+`.requires_grad_(False)`, `.to(device)`.
+
+Two semantic modes:
+  * mode="reference": the released code's behaviour — the KV cache grows inside a window and is dropped
+    with the window; memory = the first `num_history` views pooled to 196 tokens each
+    (stream_video_vln.py:102-142).  Token stream, positions and greedy outputs match the CPU oracle.
+  * mode="slowfast": the north-star semantics — voxel-pruned slow memory spliced into a live,
+    turn-granular sliding KV window with in-place compaction and RoPE re-rotation.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from types import SimpleNamespace
+from typing import Any, Dict, List, Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import check, cur_stream, ptr
+from .qwen2 import Chunk, Qwen2Config, Qwen2Engine, Qwen2Weights
+from .vision import VisionConfig, VisionFrontEnd
+from .voxel import INVALID_KEEP, VoxelPruneConfig, VoxelPruner
+
+IGNORE_INDEX = -100          # streamvln/utils/utils.py:8-16
+IMAGE_TOKEN_INDEX = -200
+MEMORY_TOKEN_INDEX = -300
+
+
+@dataclass
+class StreamVLNConfig:
+    llm: Qwen2Config = field(default_factory=Qwen2Config.qwen2_7b)
+    vision: VisionConfig = field(default_factory=VisionConfig)
+    num_history: Optional[int] = 8
+    eos_token_id: Optional[int] = None       # <|im_end|> with a real tokenizer; None = run to max_new_tokens
+    tokenizer_model_max_length: Optional[int] = None
+    mode: str = "reference"                  # "reference" | "slowfast"
+    # slowfast only
+    window_turns: int = 8                    # num_frames / num_future_steps
+    voxel_size: float = 0.2
+    max_depth: float = 10.0
+    invalid_policy: int = INVALID_KEEP
+    memory_cap: int = 1568                   # max memory tokens kept (oldest dropped first)
+
+    @staticmethod
+    def tiny(vocab_size: int = 512, mode: str = "reference", layers: int = 2, max_pos: int = 4096) -> "StreamVLNConfig":
+        llm = Qwen2Config.tiny(vocab_size, layers, max_pos)
+        return StreamVLNConfig(llm=llm, vision=VisionConfig.tiny(llm.hidden_size), mode=mode)
+
+
+class KvHandle:
+    """Opaque `past_key_values`: the arena owns the data; the handle only names the stream."""
+
+    def __init__(self, env: int, length: int):
+        self.env, self.length = env, length
+
+    def get_seq_length(self) -> int:
+        return self.length
+
+    def __repr__(self):
+        return f"KvHandle(env={self.env}, length={self.length})"
+
+
+class GenerateOutput(SimpleNamespace):
+    pass
+
+
+class _Inner:
+    """`.model` of the reference object: only `num_history` is touched by callers (streamvln_eval.py:531)."""
+
+    def __init__(self, num_history):
+        self.num_history = num_history
+
+
+class StreamVLNForCausalLM:
+    def __init__(self, config: StreamVLNConfig, weights: Optional[Qwen2Weights] = None, vision: Optional[VisionFrontEnd] = None,
+                 n_env: int = 1, device="cuda", seed: int = 0, lm_head_std: Optional[float] = None):
+        self.config = config
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("streamvln_b200 needs a CUDA device (sm_100a kernels; no CPU fallback)")
+        self.lib = _lib.load()
+        self.model = _Inner(config.num_history)
+        self.weights = weights or Qwen2Weights.random(config.llm, self.device, seed=seed, lm_head_std=lm_head_std)
+        self.vision = vision or VisionFrontEnd(config.vision, self.device, seed=seed + 1)
+        self.engine = Qwen2Engine(config.llm, self.weights, n_env=n_env, device=self.device)
+        self.tokens_per_frame = config.vision.pooled_per_side ** 2
+        self.reset(n_env)
+
+    # ------------------------------------------------------------------ reference object surface
+    def get_model(self):
+        return self.model
+
+    def get_vision_tower(self):
+        return self.vision
+
+    def eval(self):
+        return self
+
+    def requires_grad_(self, flag: bool = False):
+        return self
+
+    def to(self, *args, **kwargs):
+        return self
+
+    def reset(self, env_num: int) -> None:
+        """stream_video_vln.py:473-475 (without the `[dict()] * n` aliasing)."""
+        if env_num > self.engine.arena.n_env:
+            self.engine = Qwen2Engine(self.config.llm, self.weights, n_env=env_num, device=self.device)
+        self.curr_t = [0] * env_num
+        self.cache: List[Dict[str, Any]] = [dict() for _ in range(env_num)]
+        self.feat_cache: List[Dict[int, torch.Tensor]] = [dict() for _ in range(env_num)]
+        for e in range(env_num):
+            self.engine.arena.reset_env(e)
+        if self.config.mode == "slowfast":
+            from .slowfast import SlowFastState
+
+            self.sf = [SlowFastState(self, e) for e in range(env_num)]
+
+    def reset_for_env(self, env_idx: int) -> None:
+        """stream_video_vln.py:477-479: forget the stream's embeds (the KV goes with `past_key_values=None`)."""
+        self.curr_t[env_idx] = 0
+        self.cache[env_idx] = dict()
+        if self.config.mode == "slowfast":
+            self.sf[env_idx].reset()
+            self.engine.arena.reset_env(env_idx)
+            self.feat_cache[env_idx] = dict()
+
+    def reset_episode(self, env_idx: int) -> None:
+        """New episode on this stream: also drop the per-frame feature cache."""
+        self.reset_for_env(env_idx)
+        self.feat_cache[env_idx] = dict()
+        self.engine.arena.reset_env(env_idx)
+
+    # ------------------------------------------------------------------ encode_rgbd
+    @torch.no_grad()
+    def encode_rgbd(self, images: torch.Tensor, depths, poses, intrinsics, time_ids=None, task_ids=None,
+                    env_id: int = 0, frame_ids: Optional[Sequence[int]] = None):
+        """stream_video_vln.py:102-142 for batch size 1: returns (image_features [V',196,D],
+        memory_features [1, nh*196, D] or None).  `frame_ids` (optional, one global frame index per view)
+        enables the per-frame pooled-feature cache."""
+        assert images.shape[0] == 1, "one stream per call (the reference call sites use batch size 1)"
+        V = images.shape[1]
+        feats = self._encode_views(images[0], env_id, frame_ids)
+        start_idx = 0
+        if time_ids is not None and time_ids[0] is not None and len(time_ids[0]):
+            start_idx = time_ids[0][0]
+        if V != 1 and start_idx != 0:
+            nh = self.model.num_history
+            memory = feats[:nh].reshape(1, -1, feats.shape[-1])
+            return feats[nh:], memory
+        return feats, None
+
+    def _encode_views(self, views: torch.Tensor, env_id: int, frame_ids) -> torch.Tensor:
+        if frame_ids is None:
+            return self.vision(views.to(self.device))
+        cache = self.feat_cache[env_id]
+        missing = [i for i, f in enumerate(frame_ids) if f not in cache]
+        if missing:
+            new = self.vision(views[missing].to(self.device))
+            for j, i in enumerate(missing):
+                cache[frame_ids[i]] = new[j]
+        return torch.stack([cache[f] for f in frame_ids])
+
+    # ------------------------------------------------------------------ embed splice
+    def splice(self, input_ids: Sequence[int], image_features: torch.Tensor, memory_features: Optional[torch.Tensor]) -> torch.Tensor:
+        """prepare_inputs_labels_for_multimodal (stream_video_vln.py:144-291), inference path, one sample:
+        every IMAGE_TOKEN_INDEX is replaced by the next frame's 196 rows, every MEMORY_TOKEN_INDEX by the
+        next memory block, in order of appearance.  One gather kernel instead of the Python cat loop."""
+        tpf = image_features.shape[1] if image_features.numel() else self.tokens_per_frame
+        D = self.config.llm.hidden_size
+        blocks = [image_features.reshape(-1, D)]
+        mem_base = blocks[0].shape[0]
+        mem_rows = 0
+        if memory_features is not None:
+            blocks.append(memory_features.reshape(-1, D))
+            mem_rows = blocks[1].shape[0]
+        feat = torch.cat(blocks) if len(blocks) > 1 else blocks[0]
+        n_img = image_features.shape[0]
+        n_mem = 0 if memory_features is None else memory_features.shape[0]
+        row_src: List[int] = []
+        img_i = mem_i = 0
+        for tid in input_ids:
+            if tid == IMAGE_TOKEN_INDEX:
+                if img_i >= n_img:
+                    raise IndexError("more <image> placeholders than encoded frames")
+                row_src.extend(range(-(img_i * tpf) - 1, -((img_i + 1) * tpf) - 1, -1))
+                img_i += 1
+            elif tid == MEMORY_TOKEN_INDEX:
+                if mem_i >= n_mem:
+                    raise IndexError("more <memory> placeholders than memory blocks")
+                per = mem_rows // n_mem
+                row_src.extend(range(-(mem_base + mem_i * per) - 1, -(mem_base + (mem_i + 1) * per) - 1, -1))
+                mem_i += 1
+            elif tid < 0:
+                raise NotImplementedError(f"unknown special token {tid}")  # stream_video_vln.py:230
+            else:
+                row_src.append(tid)
+        if self.config.tokenizer_model_max_length is not None:
+            row_src = row_src[: self.config.tokenizer_model_max_length]
+        n = len(row_src)
+        src = torch.tensor(row_src, dtype=torch.int32).to(self.device, non_blocking=True)
+        out = torch.empty(n, D, dtype=torch.bfloat16, device=self.device)
+        check(self.lib.svln_splice_rows(ptr(self.weights.embed), ptr(feat.contiguous()), ptr(src), n, D * 2, ptr(out), cur_stream()))
+        self.engine.launches += 1
+        return out
+
+    # ------------------------------------------------------------------ generate
+    @torch.no_grad()
+    def generate(self, inputs: Optional[torch.Tensor] = None, images: Optional[torch.Tensor] = None,
+                 image_sizes=None, depths: Optional[torch.Tensor] = None, poses: Optional[torch.Tensor] = None,
+                 intrinsics: Optional[torch.Tensor] = None, task_ids=None, **kwargs) -> GenerateOutput:
+        """stream_video_vln.py:353-407 + HF greedy `generate` (do_sample=False, num_beams=1)."""
+        return self.generate_batch([dict(inputs=inputs, images=images, depths=depths, poses=poses,
+                                         intrinsics=intrinsics, **kwargs)])[0]
+
+    @torch.no_grad()
+    def generate_batch(self, requests: Sequence[Dict[str, Any]]) -> List[GenerateOutput]:
+        """Several streams' turns in one packed forward (one request per env_id; same kwargs as `generate`).
+        This is what lets 64 concurrent episodes share every GEMM."""
+        tails, envs, max_new = [], [], []
+        for r in requests:
+            r = dict(r)
+            if "inputs_embeds" in r:
+                raise NotImplementedError("`inputs_embeds` is not supported")  # stream_video_vln.py:369-370
+            if r.get("do_sample", False) or r.get("num_beams", 1) != 1:
+                raise NotImplementedError("only greedy decoding (do_sample=False, num_beams=1) is supported")
+            env = r.get("env_id", 0) or 0
+            ids = r["inputs"]
+            ids = ids.reshape(-1).tolist() if torch.is_tensor(ids) else list(ids)
+            time_ids = r.get("time_ids")
+            if self.config.mode == "slowfast":
+                tail = self.sf[env].prepare_turn(ids, r)
+            else:
+                if r.get("images") is not None:
+                    img_f, mem_f = self.encode_rgbd(r["images"], r.get("depths"), r.get("poses"), r.get("intrinsics"),
+                                                    time_ids, r.get("task_type"), env, r.get("frame_ids"))
+                    emb = self.splice(ids, img_f, mem_f)
+                else:
+                    emb = self.weights.embed.index_select(0, torch.tensor(ids, dtype=torch.int64).to(self.device))
+                # per-env embed cache (stream_video_vln.py:396-401), kept as chunks: only a re-prefill reads it
+                c = self.cache[env]
+                if self.curr_t[env] == 0:
+                    c["chunks"], c["len"] = [emb], emb.shape[0]
+                else:
+                    c["chunks"].append(emb)
+                    c["len"] += emb.shape[0]
+                self.curr_t[env] += 1
+                past = r.get("past_key_values")
+                past_len = self.engine.arena.lens[env] if past is not None else 0
+                if past is None:
+                    self.engine.arena.reset_env(env)
+                # HF: cache_position = arange(L_full)[past_len:] -> only the un-cached tail is run
+                n_tail = c["len"] - past_len
+                if n_tail <= 0:
+                    raise ValueError("nothing to run: the KV cache already covers every embedded token")
+                tail = emb[emb.shape[0] - n_tail:] if n_tail <= emb.shape[0] else torch.cat(c["chunks"])[past_len:]
+            tails.append(tail)
+            envs.append(env)
+            max_new.append(int(r.get("max_new_tokens", 20)))
+        if len(set(envs)) != len(envs):
+            raise ValueError("one request per env_id in a batch")
+        n_new = max(max_new)
+        seqs = self.engine.generate(tails, envs, n_new, self.config.eos_token_id)
+        outs = []
+        for r, env, s, mn in zip(requests, envs, seqs, max_new):
+            if s.shape[0] > mn:  # a shorter budget than the batch maximum: un-feed the surplus tokens
+                self.engine.arena.lens[env] -= s.shape[0] - mn
+                s = s[:mn]
+            if self.config.mode == "slowfast":
+                self.sf[env].finish_turn(int(s.shape[0]))
+            outs.append(GenerateOutput(sequences=s.unsqueeze(0),
+                                       past_key_values=KvHandle(env, self.engine.arena.lens[env])))
+        return outs

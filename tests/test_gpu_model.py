@@ -1,0 +1,166 @@
+"""GPU parity of the whole reference-semantics turn: product (`StreamVLNForCausalLM.generate`,
+`VLNEvaluator.step`) vs the CPU oracle (reference glue restated + stock transformers Qwen2ForCausalLM).
+Tolerance (north_star): logits max rel err <= 1e-2, identical greedy tokens / actions."""
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import glue
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-2
+
+
+def _hf_from(weights, dtype=torch.float32):
+    from transformers import Qwen2Config, Qwen2ForCausalLM
+
+    c = weights.cfg
+    cfg = Qwen2Config(hidden_size=c.hidden_size, intermediate_size=c.intermediate_size, num_hidden_layers=c.num_hidden_layers,
+                      num_attention_heads=c.num_attention_heads, num_key_value_heads=c.num_key_value_heads,
+                      head_dim=c.head_dim, vocab_size=c.vocab_size, max_position_embeddings=c.max_position_embeddings,
+                      rope_theta=c.rope_theta, rms_norm_eps=c.rms_norm_eps, tie_word_embeddings=False)
+    cfg.rope_parameters = {"rope_type": "default", "rope_theta": c.rope_theta}
+    lm = Qwen2ForCausalLM(cfg)
+    missing, unexpected = lm.load_state_dict({k: v.to(dtype) for k, v in weights.to_hf_state_dict().items()}, strict=False)
+    assert not unexpected and all("rotary" in m or "inv_freq" in m for m in missing), (missing, unexpected)
+    return lm.to(dtype).eval()
+
+
+def _rel(a, b):
+    return (a.double() - b.double()).abs().max().item() / b.double().abs().max().item()
+
+
+@pytest.fixture(scope="module")
+def tiny(svln_lib, cuda):
+    from streamvln_b200.model import StreamVLNConfig, StreamVLNForCausalLM
+
+    cfg = StreamVLNConfig.tiny(vocab_size=512, layers=3)
+    m = StreamVLNForCausalLM(cfg, n_env=2, device=cuda, seed=0, lm_head_std=0.3)
+    return m, _hf_from(m.weights)
+
+
+def test_engine_prefill_and_decode_logits(tiny, cuda):
+    from streamvln_b200.qwen2 import Chunk
+
+    m, lm = tiny
+    eng = m.engine
+    g = torch.Generator().manual_seed(0)
+    D = m.config.llm.hidden_size
+    emb = (torch.randn(300, D, generator=g) * 0.05).bfloat16()
+    for env in (0, 1):
+        eng.arena.reset_env(env)
+    # two streams prefilled together (ragged: 300 and 77 tokens), then a second chunk on stream 0
+    logits = eng.forward(torch.cat([emb, emb[:77]]).to(cuda), [Chunk(0, 0, 300, 300), Chunk(1, 300, 77, 77)])
+    from transformers import DynamicCache
+
+    c0, c1 = DynamicCache(config=lm.config), DynamicCache(config=lm.config)
+    with torch.no_grad():
+        w0 = lm(inputs_embeds=emb[None].float(), past_key_values=c0, use_cache=True).logits[0, -1]
+        w1 = lm(inputs_embeds=emb[None, :77].float(), past_key_values=c1, use_cache=True).logits[0, -1]
+    assert _rel(logits[0].cpu(), w0) <= TOL and _rel(logits[1].cpu(), w1) <= TOL
+    logits = eng.forward(emb[100:140].clone().to(cuda), [Chunk(0, 0, 40, 340)])
+    with torch.no_grad():
+        w0 = lm(inputs_embeds=emb[None, 100:140].float(), past_key_values=c0, use_cache=True).logits[0, -1]
+    assert _rel(logits[0].cpu(), w0) <= TOL
+    # decode: both streams step together, with and without the CUDA graph
+    tok = torch.tensor([5, 9], device=cuda)
+    for use_graph in (False, True):
+        runner = eng._decode_runner([0, 1], use_graph)
+        t = tok
+        for _ in range(3):
+            t = runner.step(t)
+        runner.finish()
+        with torch.no_grad():
+            tt = [tok[0:1].cpu(), tok[1:2].cpu()]
+            for _ in range(3):
+                tt[0] = lm(input_ids=tt[0][None], past_key_values=c0, use_cache=True).logits[0, -1:].argmax(-1)
+                tt[1] = lm(input_ids=tt[1][None], past_key_values=c1, use_cache=True).logits[0, -1:].argmax(-1)
+        assert t.cpu().tolist() == [int(tt[0]), int(tt[1])]
+        assert eng.arena.lens[0] == c0.get_seq_length() and eng.arena.lens[1] == c1.get_seq_length()
+
+
+def test_generate_matches_oracle_over_a_window_boundary(tiny, cuda):
+    m, lm = tiny
+    m.reset(2)
+    o = glue.ReferenceOracle(lm, num_history=m.model.num_history)
+    g = torch.Generator().manual_seed(1)
+    frames = (torch.randn(10, 3, 384, 384, generator=g) * 0.5)
+    feats = m.vision(frames.to(cuda))                      # [10,196,D] bf16, shared by both sides
+    feats_cpu = feats.float().cpu()
+    IMG, MEM = glue.IMAGE_TOKEN_INDEX, glue.MEMORY_TOKEN_INDEX
+    n_gen = 5
+    past_p = past_o = None
+    out_ids = None
+    worst = 0.0
+    # three ordinary turns (V=1), then a window start with num_history=8 memory views + current frame
+    plan = [([7, 8, 9, IMG, 10, 11], [0], [[0]]), (None, [1], [[0, 1, 2, 3, 4]]), (None, [2], [[0, 1, 2, 3, 4, 5, 6, 7, 8]])]
+    for ids, views, time_ids in plan:
+        if ids is None:
+            ids = out_ids + [20, IMG, 21, 22]
+        r = m.generate(inputs=torch.tensor([ids]), images=frames[views][None], env_id=1, time_ids=time_ids,
+                       frame_ids=views, do_sample=False, num_beams=1, max_new_tokens=n_gen, use_cache=True,
+                       return_dict_in_generate=True, past_key_values=past_p)
+        seq_o, past_o, logits_o = o.generate(ids, feats_cpu[views], time_ids, 0, past_o, n_gen)
+        past_p = r.past_key_values
+        assert r.sequences.shape == (1, n_gen)
+        assert r.sequences.cpu().tolist() == seq_o.tolist()
+        assert past_p.get_seq_length() == past_o.get_seq_length()
+        out_ids = seq_o[0].tolist()
+    # window boundary: caller drops the cache (streamvln_agent.py:192-198)
+    m.reset_for_env(1)
+    o.reset_for_env(0)
+    ids = [7, 8, 9, 30, MEM, 31, IMG, 10, 11]
+    views = [0, 1, 2, 3, 4, 5, 6, 7, 9]
+    r = m.generate(inputs=torch.tensor([ids]), images=frames[views][None], env_id=1, time_ids=[[32]], frame_ids=views,
+                   max_new_tokens=n_gen, past_key_values=None)
+    seq_o, past_o, logits_o = o.generate(ids, feats_cpu[views], [[32]], 0, None, n_gen)
+    assert r.sequences.cpu().tolist() == seq_o.tolist()
+    assert r.past_key_values.get_seq_length() == past_o.get_seq_length() == len(ids) - 2 + 9 * 196 + n_gen - 1
+
+
+def test_first_step_logits_tolerance(tiny, cuda):
+    """Logits of a window-start prefill (1.7k tokens through the tcgen05 kernel) within 1e-2 of the oracle."""
+    from streamvln_b200.qwen2 import Chunk
+
+    m, lm = tiny
+    m.reset(2)
+    feats = (torch.randn(9, 196, m.config.llm.hidden_size, generator=torch.Generator().manual_seed(2)) * 0.05).bfloat16()
+    ids = [7, 8, 9, 30, glue.MEMORY_TOKEN_INDEX, 31, glue.IMAGE_TOKEN_INDEX, 10, 11]
+    emb = m.splice(ids, feats[8:].to(cuda), feats[:8].reshape(1, -1, feats.shape[-1]).to(cuda))
+    want_emb = glue.splice(ids, m.weights.embed.float().cpu(), feats[8:].float(), feats[:8].reshape(1, -1, feats.shape[-1]).float())
+    assert torch.equal(emb.float().cpu(), want_emb)       # the splice kernel is a pure gather: bit-exact
+    logits = m.engine.forward(emb, [Chunk(0, 0, emb.shape[0], emb.shape[0])])
+    with torch.no_grad():
+        want = lm(inputs_embeds=want_emb[None]).logits[0, -1]
+    assert _rel(logits[0].cpu(), want) <= TOL
+    assert int(logits[0].argmax()) == int(want.argmax())
+
+
+def test_agent_actions_match_oracle_agent(tiny, cuda):
+    """40 env steps (model turn every 4th frame, window reset at 32) through VLNEvaluator.step."""
+    from streamvln_b200.agent import VLNEvaluator
+    from streamvln_b200.synth import intrinsic_matrix
+    from streamvln_b200.tokenizer import StubQwenTokenizer
+
+    m, lm = tiny
+    m.reset(1)
+    args = SimpleNamespace(num_frames=32, num_future_steps=4, num_history=8, max_new_tokens=4)
+    ev = VLNEvaluator({"camera_intrinsic": intrinsic_matrix()}, model=m, tokenizer=StubQwenTokenizer(512), args=args)
+    rng = np.random.default_rng(0)
+    frames = rng.integers(0, 255, size=(40, 480, 640, 3), dtype=np.uint8)
+    got = []
+    for s in range(40):
+        a, _, txt = ev.step(0, frames[s], "walk past the sofa and stop at the door", run_model=(s % 4 == 0))
+        got.append(a)
+        ev.step_id += 1
+    o = glue.ReferenceOracle(lm, num_history=8)
+    oa = glue.OracleAgent(o, StubQwenTokenizer(512), lambda i: m.feat_cache[0][i].float().cpu(), 32, 4, 8, 4)
+    want = []
+    for s in range(40):
+        want.append(oa.step(0, "walk past the sofa and stop at the door", run_model=(s % 4 == 0)))
+        oa.step_id += 1
+    assert got == want
+    assert sum(a is not None for a in got) == 10
