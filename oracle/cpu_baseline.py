@@ -59,6 +59,7 @@ def build_reference_cpu(sample_layers: int = 4, full_layers: int = 28, dtype=tor
             else:
                 p.data.zero_()
         vis.vision_model.head = torch.nn.Identity()
+        vis.vision_model.embeddings.position_ids = torch.arange(729)[None]  # buffer was created on meta
         vis.eval()
     proj = (torch.empty(3584, 1152, dtype=dtype).uniform_(-0.035, 0.035), torch.zeros(3584, dtype=dtype),
             torch.empty(3584, 3584, dtype=dtype).uniform_(-0.035, 0.035), torch.zeros(3584, dtype=dtype))

@@ -111,8 +111,11 @@ class VLNEvaluator:
         return torch.tensor(input_ids, dtype=torch.long), conversations
 
     # ------------------------------------------------------------------------------------------
-    def step(self, idx, rgb, instruction_text: str = "", run_model: bool = False, depth=None, pose=None, intrinsic=None):
-        """streamvln_agent.py:169-258.  Returns (action_seq | None, generate_time, llm_outputs | None)."""
+    def step(self, idx, rgb, instruction_text: str = "", run_model: bool = False, depth=None, pose=None, intrinsic=None,
+             preprocessed: Optional[torch.Tensor] = None):
+        """streamvln_agent.py:169-258.  Returns (action_seq | None, generate_time, llm_outputs | None).
+        `preprocessed` (optional [3,384,384] tensor, host or device) bypasses the PIL image processor — used
+        when frames are already resident in HBM."""
         # Step 0: observations (faked like the reference unless the caller supplies real geometry)
         camera_pose = np.eye(4) if pose is None else np.asarray(pose)
         depth = np.zeros((self.image_processor.crop_size["height"], self.image_processor.crop_size["width"]), np.float32) \
@@ -120,9 +123,12 @@ class VLNEvaluator:
         intrinsic = torch.from_numpy(np.asarray(self.intrinsic_matrix if intrinsic is None else intrinsic)).float()
         # Step 1: preprocess the image only on model steps; other steps repeat the last one (:177-184)
         if run_model:
-            from PIL import Image
+            if preprocessed is not None:
+                image = preprocessed
+            else:
+                from PIL import Image
 
-            image = self.image_processor.preprocess(images=Image.fromarray(rgb).convert("RGB"), return_tensors="pt")["pixel_values"][0]
+                image = self.image_processor.preprocess(images=Image.fromarray(rgb).convert("RGB"), return_tensors="pt")["pixel_values"][0]
             self.last_image = image
         else:
             image = self.last_image
@@ -173,13 +179,17 @@ class VLNEvaluator:
         frame_ids = [self._source_frame(i) for i in sel]
         # Step 4: generate (:242-246).  One pinned-memory H2D per turn for the frames.
         tt = time.time()
-        images = images.pin_memory().to(self.device, non_blocking=True)
+        self.h2d_bytes = 0
+        if not images.is_cuda:
+            self.h2d_bytes = images.numel() * images.element_size() + input_ids.numel() * 8
+            images = images.pin_memory().to(self.device, non_blocking=True)
         outputs = self.model.generate(inputs=input_ids, images=images, depths=depths, poses=poses, intrinsics=intrinsics,
                                       env_id=idx, time_ids=[self.time_ids], task_ids=[0], frame_ids=frame_ids,
                                       do_sample=False, num_beams=1, max_new_tokens=self.max_new_tokens, use_cache=True,
                                       return_dict_in_generate=True, past_key_values=self.past_key_values)
         self.output_ids = outputs.sequences
         ids_host = self.output_ids.cpu()  # the D2H read of the turn's result
+        self.d2h_bytes = ids_host.numel() * 8
         generate_time = time.time() - tt
         # Step 5: decode + parse (:248-258)
         llm_outputs = self.tokenizer.batch_decode(ids_host, skip_special_tokens=False)[0].strip()

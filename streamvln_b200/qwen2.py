@@ -139,6 +139,7 @@ class Qwen2Engine:
                              cfg.max_position_embeddings, cfg.rope_theta, self.device)
         self.scale = cfg.head_dim ** -0.5
         self.launches = 0  # libsvln kernel launches (bench.py reports them as gpu_launches)
+        self.prof = None   # bench.py: dict name -> [(start_event, end_event, algorithmic_work)] when profiling
         self._graphs: Dict[int, "_DecodeGraph"] = {}
 
     # ------------------------------------------------------------------ small kernels
@@ -220,8 +221,18 @@ class Qwen2Engine:
             se, qs = [c.env for c in chunks], [c.q_start for c in chunks]
             nq, kl = [c.n_q for c in chunks], [c.kv_len for c in chunks]
 
+            # algorithmic FLOPs of one launch: Hq * 4 * d * n_q * (P + n_q / 2) per chunk
+            flops = sum(self.cfg.num_attention_heads * 4 * self.cfg.head_dim * c.n_q * ((c.kv_len - c.n_q) + c.n_q / 2)
+                        for c in chunks)
+
             def attn(li, q, out):
+                if self.prof is not None:
+                    s_ev, e_ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    s_ev.record()
                 self.arena.attn_prefill(li, q, self.cfg.num_attention_heads, se, qs, nq, kl, self.scale, out)
+                if self.prof is not None:
+                    e_ev.record()
+                    self.prof.setdefault("attn_prefill", []).append((s_ev, e_ev, flops))
                 self.launches += 1
         h, pending = self._layers(h, tok_env, tok_pos, attn)
         for c in chunks:
