@@ -1,0 +1,98 @@
+"""GPU parity of mode="slowfast" (voxel-pruned memory + sliding KV window with in-place compaction and RoPE
+re-rotation) against oracle/slowfast.py: bit-exact memory sets and cache layout, identical greedy tokens,
+first-step logits within 1e-2."""
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import glue
+from oracle.slowfast import SlowFastOracle
+
+pytestmark = pytest.mark.gpu
+IMG, MEM = glue.IMAGE_TOKEN_INDEX, glue.MEMORY_TOKEN_INDEX
+
+
+def _rel(a, b):
+    return (a.double() - b.double()).abs().max().item() / b.double().abs().max().item()
+
+
+@pytest.mark.parametrize("window_turns,memory_cap,policy", [(3, 1568, 0), (2, 300, 1)])
+def test_slowfast_turns_match_oracle(svln_lib, cuda, window_turns, memory_cap, policy):
+    from streamvln_b200 import synth
+    from streamvln_b200.model import StreamVLNConfig, StreamVLNForCausalLM
+    from test_gpu_model import _hf_from
+
+    cfg = StreamVLNConfig.tiny(vocab_size=512, mode="slowfast", layers=3)
+    cfg.window_turns, cfg.memory_cap, cfg.invalid_policy, cfg.voxel_size = window_turns, memory_cap, policy, 0.25
+    m = StreamVLNForCausalLM(cfg, n_env=1, device=cuda, seed=0, lm_head_std=0.3)
+    lm = _hf_from(m.weights)
+    o = SlowFastOracle(lm, 14, window_turns, 0.25, 10.0, policy, memory_cap)
+    n_turns, n_gen = 9, 4
+    st = synth.make_stream(n_turns * 4, 14, 8, seed=5, with_feat=False)
+    frames = torch.randn(n_turns, 3, 384, 384, generator=torch.Generator().manual_seed(3)) * 0.5
+    feats = m.vision(frames.to(cuda)).float().cpu()
+    out_ids = None
+    past = None
+    worst = 0.0
+    for k in range(n_turns):
+        t = 4 * k
+        if k == 0:
+            ids = [7, 8, 9, 30, MEM, 31, 32, IMG, 10, 11]
+        else:
+            ids = out_ids + [20, 21, IMG, 22, 23]
+        depth, pose, intr = st["depth"][t], st["pose"][t], st["intr"][t]
+        r = m.generate(inputs=torch.tensor([ids]), images=frames[k][None, None], depths=torch.from_numpy(depth)[None, None],
+                       poses=torch.from_numpy(pose)[None, None], intrinsics=torch.from_numpy(intr)[None, None], env_id=0,
+                       time_ids=[[t]], frame_ids=[k], max_new_tokens=n_gen, past_key_values=past)
+        past = r.past_key_values
+        seq_o = o.generate(list(ids), feats[k:k + 1], depth, pose, intr, t, n_gen)
+        assert r.sequences.cpu().tolist() == seq_o.tolist(), f"turn {k}"
+        out_ids = seq_o[0].tolist()
+        sf = m.sf[0]
+        # integer state: bit-exact
+        assert m.engine.arena.lens[0] == o.cache.get_seq_length(), f"turn {k}"
+        assert np.array_equal(sf.mem_keys.cpu().numpy(), o.mem_keys) and np.array_equal(sf.mem_t.cpu().numpy(), o.mem_t)
+        assert [(u.row_start, u.n_rows) for u in sf.turns] == [(u["row_start"], u["n_rows"]) for u in o.turns]
+        assert len(sf.turns) <= window_turns and sf.mem_keys.numel() <= memory_cap
+    assert sf.evictions == n_turns - window_turns
+    # K/V rows of the live cache agree with the oracle's (bf16 vs fp32 + re-rotation rounding)
+    L = m.engine.arena.lens[0]
+    for layer in range(cfg.llm.num_hidden_layers):
+        kp = m.engine.arena.plane(0, layer, 0)[:, :L].float().cpu()
+        vp = m.engine.arena.plane(0, layer, 1)[:, :L].float().cpu()
+        assert _rel(kp, o.cache.layers[layer].keys[0]) <= 2e-2
+        assert _rel(vp, o.cache.layers[layer].values[0]) <= 2e-2
+    assert o.mem_keys.shape[0] > 0
+
+
+def test_slowfast_agent_long_horizon(svln_lib, cuda):
+    """RxR-shaped long stream through VLNEvaluator.step: the cache stays bounded, memory is deduplicated."""
+    from streamvln_b200 import synth
+    from streamvln_b200.agent import VLNEvaluator
+    from streamvln_b200.model import StreamVLNConfig, StreamVLNForCausalLM
+    from streamvln_b200.tokenizer import StubQwenTokenizer
+
+    cfg = StreamVLNConfig.tiny(vocab_size=512, mode="slowfast", layers=2)
+    cfg.window_turns, cfg.memory_cap, cfg.invalid_policy = 4, 800, 1
+    m = StreamVLNForCausalLM(cfg, n_env=1, device=cuda, seed=1)
+    args = SimpleNamespace(num_frames=32, num_future_steps=4, num_history=8, max_new_tokens=4)
+    ev = VLNEvaluator({"camera_intrinsic": synth.intrinsic_matrix()}, model=m, tokenizer=StubQwenTokenizer(512), args=args)
+    n_steps = 120
+    st = synth.make_stream(n_steps, 14, 8, seed=2, with_feat=False)
+    frames = np.random.default_rng(0).integers(0, 255, size=(8, 480, 640, 3), dtype=np.uint8)
+    lens = []
+    for s in range(n_steps):
+        a, _, _ = ev.step(0, frames[s % 8], "go to the kitchen", run_model=(s % 4 == 0), depth=st["depth"][s],
+                          pose=st["pose"][s], intrinsic=st["intr"][s])
+        if s % 4 == 0:
+            assert a and all(x in (0, 1, 2, 3) for x in a)
+            lens.append(m.engine.arena.lens[0])
+        ev.step_id += 1
+    sf = m.sf[0]
+    assert sf.evictions == 30 - 4
+    assert max(lens) < 4096 and sf.mem_keys.numel() <= 800
+    k = sf.mem_keys[sf.mem_keys >= 0]
+    assert k.unique().numel() == k.numel()          # one survivor per voxel
+    assert torch.all(sf.mem_t[1:] >= sf.mem_t[:-1])  # stable order: oldest first
