@@ -180,12 +180,15 @@ def main_ours(a):
     # ---- device-resident arm
     agent.reset_memory()
     run_turns(agent, W, frames_host, frames_dev, True, geom)
-    model.engine.prof = {}
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     ms, launches, _, _ = timed(agent, model, K, frames_host, frames_dev, True, dist, device, geom)
     clocks = sampler.stop() if rank == 0 else None
+    # ---- same K turns once more with CUDA events around every prefill-attention launch (events cannot be
+    #      recorded inside a replayed CUDA graph, so this pass launches the kernels eagerly)
+    model.engine.prof = {}
+    ms_prof, _, _, _ = timed(agent, model, K, frames_host, frames_dev, True, dist, device, geom)
     prof, model.engine.prof = model.engine.prof, None
     # ---- end-to-end arm (host uint8 frames through the public agent API)
     agent.reset_memory()
@@ -205,8 +208,9 @@ def main_ours(a):
         roof = {"kernel": "attn_prefill_kernel (tcgen05/TMEM, TMA-fed)", "bound": "tensor", "achieved": round(ach, 2),
                 "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": round(ach / pk["bf16_tflops_sustained"], 4),
                 "traffic": None, "launches": len(ev), "avg_launch_us": round(1e3 * t_ms / len(ev), 2),
-                "share_of_step": round(t_ms / ms, 4), "peak_source": pk["source"] + " (sustained: kernel timed inside a long step)",
-                "note": "single-episode turn: ~217 new tokens x 7 GQA heads = 12 M-tiles x 4 kv heads = 48 CTAs on 148 SMs"}
+                "share_of_step": round(t_ms / ms_prof, 4), "peak_source": pk["source"] + " (sustained: kernel timed inside a long step)",
+                "note": "single-episode turn: ~217 new tokens x 7 GQA heads = 12 M-tiles x 4 kv heads = 48 CTAs on 148 SMs; "
+                        "timed in a second pass of the same K turns with eager launches (events cannot sit inside a CUDA graph)"}
     out = {
         "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": round(ms / K, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

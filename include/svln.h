@@ -201,6 +201,14 @@ int svln_attn_prefill(const svln_kv_arena* arena, int layer, const void* q, int 
                       float scale, void* workspace, size_t workspace_bytes, void* out,
                       svln_stream_t stream);
 
+/* Same kernel with the sequence descriptors in DEVICE memory (seq_env / q_start / n_q / kv_len, i32 [n_seq]),
+ * so that a captured CUDA graph can be replayed with new cache lengths; only n_q (host copy, sizes the grid)
+ * is baked into the launch and must equal the device n_q. */
+int svln_attn_prefill_dev(const svln_kv_arena* arena, int layer, const void* q, int n_q_head,
+                          const int32_t* seq_env, const int32_t* q_start, const int32_t* n_q,
+                          const int32_t* kv_len, const int32_t* n_q_host, int n_seq, float scale,
+                          void* out, svln_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * Small fused ops around the Qwen2 linears (which stay cuBLAS): HF Qwen2RMSNorm and the
  * SwiGLU product, with HF's bf16 rounding points.

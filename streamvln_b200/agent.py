@@ -111,11 +111,10 @@ class VLNEvaluator:
         return torch.tensor(input_ids, dtype=torch.long), conversations
 
     # ------------------------------------------------------------------------------------------
-    def step(self, idx, rgb, instruction_text: str = "", run_model: bool = False, depth=None, pose=None, intrinsic=None,
-             preprocessed: Optional[torch.Tensor] = None):
-        """streamvln_agent.py:169-258.  Returns (action_seq | None, generate_time, llm_outputs | None).
-        `preprocessed` (optional [3,384,384] tensor, host or device) bypasses the PIL image processor — used
-        when frames are already resident in HBM."""
+    def prepare(self, idx, rgb, instruction_text: str = "", run_model: bool = False, depth=None, pose=None, intrinsic=None,
+                preprocessed: Optional[torch.Tensor] = None):
+        """First half of `step` (streamvln_agent.py:169-240): buffer the frame, handle the window boundary, and on
+        a model step build the kwargs of `model.generate`.  Returns None on a non-model step."""
         # Step 0: observations (faked like the reference unless the caller supplies real geometry)
         camera_pose = np.eye(4) if pose is None else np.asarray(pose)
         depth = np.zeros((self.image_processor.crop_size["height"], self.image_processor.crop_size["width"]), np.float32) \
@@ -144,7 +143,7 @@ class VLNEvaluator:
                 self.output_ids = None
                 self.past_key_values = None
                 self.time_ids = []
-            return None, 0, None
+            return None
         # Step 3: prompt (:201-217)
         if self.output_ids is None:
             sources = copy.deepcopy(self.conversation)
@@ -178,26 +177,39 @@ class VLNEvaluator:
         # frames repeated on non-model steps are the same image: key the feature cache by the model-step frame
         frame_ids = [self._source_frame(i) for i in sel]
         # Step 4: generate (:242-246).  One pinned-memory H2D per turn for the frames.
-        tt = time.time()
         self.h2d_bytes = 0
         if not images.is_cuda:
             self.h2d_bytes = images.numel() * images.element_size() + input_ids.numel() * 8
             images = images.pin_memory().to(self.device, non_blocking=True)
-        outputs = self.model.generate(inputs=input_ids, images=images, depths=depths, poses=poses, intrinsics=intrinsics,
-                                      env_id=idx, time_ids=[self.time_ids], task_ids=[0], frame_ids=frame_ids,
-                                      do_sample=False, num_beams=1, max_new_tokens=self.max_new_tokens, use_cache=True,
-                                      return_dict_in_generate=True, past_key_values=self.past_key_values)
+        return dict(inputs=input_ids, images=images, depths=depths, poses=poses, intrinsics=intrinsics, env_id=idx,
+                    time_ids=[list(self.time_ids)], task_ids=[0], frame_ids=frame_ids, do_sample=False, num_beams=1,
+                    max_new_tokens=self.max_new_tokens, use_cache=True, return_dict_in_generate=True,
+                    past_key_values=self.past_key_values)
+
+    def finish(self, outputs):
+        """Second half of `step` (:247-258): keep ids + cache handle, decode, parse the actions."""
         self.output_ids = outputs.sequences
         ids_host = self.output_ids.cpu()  # the D2H read of the turn's result
         self.d2h_bytes = ids_host.numel() * 8
-        generate_time = time.time() - tt
-        # Step 5: decode + parse (:248-258)
         llm_outputs = self.tokenizer.batch_decode(ids_host, skip_special_tokens=False)[0].strip()
         self.past_key_values = outputs.past_key_values
         action_seq = self.parse_actions(llm_outputs)
         if len(action_seq) == 0:
             action_seq = [0]
-        return action_seq, generate_time, llm_outputs
+        return action_seq, llm_outputs
+
+    def step(self, idx, rgb, instruction_text: str = "", run_model: bool = False, depth=None, pose=None, intrinsic=None,
+             preprocessed: Optional[torch.Tensor] = None):
+        """streamvln_agent.py:169-258.  Returns (action_seq | None, generate_time, llm_outputs | None).
+        `preprocessed` (optional [3,384,384] tensor, host or device) bypasses the PIL image processor — used
+        when frames are already resident in HBM."""
+        req = self.prepare(idx, rgb, instruction_text, run_model, depth, pose, intrinsic, preprocessed)
+        if req is None:
+            return None, 0, None
+        tt = time.time()
+        outputs = self.model.generate(**req)
+        action_seq, llm_outputs = self.finish(outputs)
+        return action_seq, time.time() - tt, llm_outputs
 
     def _source_frame(self, i: int) -> int:
         """Index of the model-step frame whose preprocessed image frame i repeats (identity lookup)."""

@@ -286,34 +286,49 @@ attn_decode_kernel(const DecodeParams p) {
     }
 }
 
-// combine the split partials of one (row group, kv head); 128 threads = 128 dims
+// combine the split partials of one row of one (row group, kv head); 128 threads = 128 dims.
+// Split weights are computed once, cooperatively, into shared memory; the accumulation loop then
+// issues independent loads (no dependent global reads), so it pipelines.
+constexpr int MAX_SPLITS = 64;
+
 __global__ void __launch_bounds__(HD)
 attn_decode_combine_kernel(const DecodeParams p) {
-    const int kvh = blockIdx.y;
+    __shared__ float s_w[MAX_SPLITS];
+    __shared__ float s_red[4];
+    const int kvh = blockIdx.y, r = blockIdx.z;
     const int b = blockIdx.x / p.groups_per_seq, grp = blockIdx.x % p.groups_per_seq;
     const int g = p.n_q_head / p.arena.n_kv_head;
     const int nq = p.n_q[b], qs = p.q_start[b];
     const int tok0 = grp * p.tok_per_group;
     if (tok0 >= nq) return;
     const int ntok = min(p.tok_per_group, nq - tok0);
-    const int rows_valid = ntok * g;
+    if (r >= ntok * g) return;
     const int64_t slot0 = ((int64_t)blockIdx.x * p.arena.n_kv_head + kvh) * p.n_splits;
-    const int d = threadIdx.x;
-    for (int r = 0; r < rows_valid; ++r) {
-        float m = -INFINITY;
-        for (int s = 0; s < p.n_splits; ++s) m = fmaxf(m, p.part_m[(slot0 + s) * DROWS + r]);
-        float acc = 0.f, l = 0.f;
-        for (int s = 0; s < p.n_splits; ++s) {
-            const float ms = p.part_m[(slot0 + s) * DROWS + r];
-            if (ms == -INFINITY) continue;
-            const float f = exp2f((ms - m) * p.scale_log2);
-            acc += p.part_o[((slot0 + s) * DROWS + r) * HD + d] * f;
-            l += p.part_l[(slot0 + s) * DROWS + r] * f;
-        }
-        const int tq = tok0 + r / g, hq = kvh * g + r % g;
-        const float val = l > 0.f ? acc / l : 0.f;
-        p.out[((int64_t)(qs + tq) * p.n_q_head + hq) * HD + d] = __float2bfloat16_rn(val);
+    const int d = threadIdx.x, lane = d & 31, warp = d >> 5;
+    // n_splits <= MAX_SPLITS <= 128 threads: thread s owns split s
+    const float ms = d < p.n_splits ? p.part_m[(slot0 + d) * DROWS + r] : -INFINITY;
+    float m = warp_max(ms);
+    if (lane == 0) s_red[warp] = m;
+    __syncthreads();
+    m = fmaxf(fmaxf(s_red[0], s_red[1]), fmaxf(s_red[2], s_red[3]));
+    const float w = (d < p.n_splits && ms != -INFINITY) ? exp2f((ms - m) * p.scale_log2) : 0.f;
+    if (d < p.n_splits) s_w[d] = w;
+    float l = d < p.n_splits ? p.part_l[(slot0 + d) * DROWS + r] * w : 0.f;
+    l = warp_sum(l);
+    __syncthreads();
+    if (lane == 0) s_red[warp] = l;
+    __syncthreads();
+    l = s_red[0] + s_red[1] + s_red[2] + s_red[3];
+    float acc = 0.f;
+    const float* po = p.part_o + (slot0 * DROWS + r) * HD + d;
+#pragma unroll 4
+    for (int s = 0; s < p.n_splits; ++s) {
+        const float ws = s_w[s];
+        if (ws != 0.f) acc += po[(int64_t)s * DROWS * HD] * ws;  // empty splits never wrote part_o
     }
+    const int tq = tok0 + r / g, hq = kvh * g + r % g;
+    const float val = l > 0.f ? acc / l : 0.f;
+    p.out[((int64_t)(qs + tq) * p.n_q_head + hq) * HD + d] = __float2bfloat16_rn(val);
 }
 
 }  // namespace svln
@@ -356,11 +371,13 @@ int svln_attn_decode(const svln_kv_arena* arena, int layer, const void* q, int n
     const int64_t groups = (int64_t)n_seq * p.groups_per_seq;
     const int64_t base_ctas = groups * arena->n_kv_head;
     const int tiles = (max_kv_len + DT - 1) / DT;
-    // aim for ~2 CTAs per SM (96 KB smem each); never split below one tile
+    // aim for ~2 CTAs per SM (96 KB smem each), but give every CTA at least 4 tiles (256 keys, 128 KB of
+    // K+V) so the per-CTA prologue / merge / partial write is amortised; at most MAX_SPLITS splits
     int64_t want = (2ll * sm_count() + base_ctas - 1) / base_ctas;
     if (want < 1) want = 1;
-    if (want > tiles) want = tiles;
-    const int tiles_per_split = (int)((tiles + want - 1) / want);
+    if (want > MAX_SPLITS) want = MAX_SPLITS;
+    int tiles_per_split = (int)((tiles + want - 1) / want);
+    if (tiles_per_split < 4) tiles_per_split = tiles < 4 ? tiles : 4;
     p.n_splits = (tiles + tiles_per_split - 1) / tiles_per_split;
     p.split_keys = tiles_per_split * DT;
     p.scale_log2 = scale * 1.4426950408889634f;
@@ -380,7 +397,7 @@ int svln_attn_decode(const svln_kv_arena* arena, int layer, const void* q, int n
     }
     dim3 grid(p.n_splits, arena->n_kv_head, (unsigned)groups);
     attn_decode_kernel<<<grid, DWARPS * 32, DEC_SMEM, (cudaStream_t)stream>>>(p);
-    dim3 cgrid((unsigned)groups, arena->n_kv_head);
+    dim3 cgrid((unsigned)groups, arena->n_kv_head, DROWS);
     attn_decode_combine_kernel<<<cgrid, HD, 0, (cudaStream_t)stream>>>(p);
     return check_launch("attn_decode kernels");
 }

@@ -47,8 +47,11 @@ struct PrefillParams {
     int n_q_head, n_kv_head, n_layer, layer, max_len;
     int n_seq;
     float scale_log2;
+    // sequence descriptors: device arrays when d_env != nullptr (CUDA-graph replayable: only the grid
+    // shape, i.e. n_q, is baked into the launch), else the by-value copies below
+    const int32_t *d_env, *d_q_start, *d_n_q, *d_kv_len;
     int32_t env[PF_MAX_SEQ], q_start[PF_MAX_SEQ], n_q[PF_MAX_SEQ], kv_len[PF_MAX_SEQ];
-    int32_t tile_start[PF_MAX_SEQ + 1];  // prefix sum of M tiles per sequence
+    int32_t tile_start[PF_MAX_SEQ + 1];  // prefix sum of M tiles per sequence (from the host-known n_q)
 };
 
 // ---------------------------------------------------------------------------- PTX wrappers
@@ -150,7 +153,11 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap kv_map, const __grid_con
     int b = 0;
     while (b + 1 < p.n_seq && (int)blockIdx.x >= p.tile_start[b + 1]) ++b;
     const int mtile = blockIdx.x - p.tile_start[b];
-    const int nq = p.n_q[b], len = p.kv_len[b], env = p.env[b], qs = p.q_start[b];
+    const bool dev = p.d_env != nullptr;
+    const int nq = dev ? p.d_n_q[b] : p.n_q[b];
+    const int len = dev ? p.d_kv_len[b] : p.kv_len[b];
+    const int env = dev ? p.d_env[b] : p.env[b];
+    const int qs = dev ? p.d_q_start[b] : p.q_start[b];
     const int rows_total = nq * g;
     const int row0 = mtile * PF_BM;
     const int rows_here = min(PF_BM, rows_total - row0);
@@ -415,26 +422,21 @@ static int get_kv_map(const svln_kv_arena* a, CUtensorMap* out) {
     return SVLN_OK;
 }
 
-}  // namespace svln
-
-using namespace svln;
-
-extern "C" {
-
-int svln_attn_prefill(const svln_kv_arena* arena, int layer, const void* q, int n_q_head,
-                      const int32_t* seq_env_host, const int32_t* q_start_host, const int32_t* n_q_host,
-                      const int32_t* kv_len_host, int n_seq, float scale, void* workspace, size_t workspace_bytes,
-                      void* out, svln_stream_t stream) {
-    (void)workspace; (void)workspace_bytes;
-    SVLN_REQUIRE(arena && arena->base && arena->head_dim == 128, SVLN_ERR_INVALID, "svln_attn_prefill: bad arena");
-    SVLN_REQUIRE(layer >= 0 && layer < arena->n_layer, SVLN_ERR_INVALID, "svln_attn_prefill: layer out of range");
+static int prefill_launch(const svln_kv_arena* arena, int layer, const void* q, int n_q_head, const int32_t* env_h,
+                          const int32_t* q_start_h, const int32_t* n_q_h, const int32_t* kv_len_h, const int32_t* env_d,
+                          const int32_t* q_start_d, const int32_t* n_q_d, const int32_t* kv_len_d, int n_seq, float scale,
+                          void* out, svln_stream_t stream, const char* who) {
+    SVLN_REQUIRE(arena && arena->base && arena->head_dim == 128, SVLN_ERR_INVALID, "%s: bad arena", who);
+    SVLN_REQUIRE(layer >= 0 && layer < arena->n_layer, SVLN_ERR_INVALID, "%s: layer out of range", who);
     SVLN_REQUIRE(n_q_head > 0 && n_q_head % arena->n_kv_head == 0, SVLN_ERR_INVALID,
-                 "svln_attn_prefill: n_q_head %d not a multiple of n_kv_head %d", n_q_head, arena->n_kv_head);
-    SVLN_REQUIRE(n_seq >= 0, SVLN_ERR_INVALID, "svln_attn_prefill: negative n_seq");
+                 "%s: n_q_head %d not a multiple of n_kv_head %d", who, n_q_head, arena->n_kv_head);
+    SVLN_REQUIRE(n_seq >= 0, SVLN_ERR_INVALID, "%s: negative n_seq", who);
     if (n_seq == 0) return SVLN_OK;
-    SVLN_REQUIRE(q && out && seq_env_host && q_start_host && n_q_host && kv_len_host, SVLN_ERR_INVALID,
-                 "svln_attn_prefill: null pointer");
-    SVLN_REQUIRE(((uintptr_t)arena->base & 15) == 0, SVLN_ERR_INVALID, "svln_attn_prefill: arena base must be 16-byte aligned");
+    SVLN_REQUIRE(q && out && n_q_h, SVLN_ERR_INVALID, "%s: null pointer", who);
+    SVLN_REQUIRE(((uintptr_t)arena->base & 15) == 0, SVLN_ERR_INVALID, "%s: arena base must be 16-byte aligned", who);
+    const bool dev = env_d != nullptr;
+    SVLN_REQUIRE(dev ? (q_start_d && n_q_d && kv_len_d) : (env_h && q_start_h && kv_len_h), SVLN_ERR_INVALID,
+                 "%s: null descriptor array", who);
     CUtensorMap map;
     int rc = get_kv_map(arena, &map);
     if (rc) return rc;
@@ -453,25 +455,58 @@ int svln_attn_prefill(const svln_kv_arena* arena, int layer, const void* q, int 
         p.scale_log2 = scale * 1.4426950408889634f;
         const int ns = n_seq - s0 < PF_MAX_SEQ ? n_seq - s0 : PF_MAX_SEQ;
         p.n_seq = ns;
+        p.d_env = dev ? env_d + s0 : nullptr;
+        p.d_q_start = dev ? q_start_d + s0 : nullptr;
+        p.d_n_q = dev ? n_q_d + s0 : nullptr;
+        p.d_kv_len = dev ? kv_len_d + s0 : nullptr;
         int tiles = 0;
         for (int i = 0; i < ns; ++i) {
             const int b = s0 + i;
-            SVLN_REQUIRE(seq_env_host[b] >= 0 && seq_env_host[b] < arena->n_env, SVLN_ERR_INVALID,
-                         "svln_attn_prefill: env %d out of range", seq_env_host[b]);
-            SVLN_REQUIRE(n_q_host[b] >= 1 && kv_len_host[b] >= n_q_host[b] && kv_len_host[b] <= arena->max_len,
-                         SVLN_ERR_INVALID, "svln_attn_prefill: bad lengths n_q=%d kv_len=%d", n_q_host[b], kv_len_host[b]);
-            p.env[i] = seq_env_host[b]; p.q_start[i] = q_start_host[b]; p.n_q[i] = n_q_host[b]; p.kv_len[i] = kv_len_host[b];
+            SVLN_REQUIRE(n_q_h[b] >= 1 && n_q_h[b] <= arena->max_len, SVLN_ERR_INVALID, "%s: bad n_q=%d", who, n_q_h[b]);
+            if (!dev) {
+                SVLN_REQUIRE(env_h[b] >= 0 && env_h[b] < arena->n_env, SVLN_ERR_INVALID, "%s: env %d out of range", who, env_h[b]);
+                SVLN_REQUIRE(kv_len_h[b] >= n_q_h[b] && kv_len_h[b] <= arena->max_len, SVLN_ERR_INVALID,
+                             "%s: bad lengths n_q=%d kv_len=%d", who, n_q_h[b], kv_len_h[b]);
+                p.env[i] = env_h[b]; p.q_start[i] = q_start_h[b]; p.kv_len[i] = kv_len_h[b];
+            } else {
+                p.env[i] = p.q_start[i] = p.kv_len[i] = 0;
+            }
+            p.n_q[i] = n_q_h[b];
             p.tile_start[i] = tiles;
-            tiles += (n_q_host[b] * g + PF_BM - 1) / PF_BM;
+            tiles += (n_q_h[b] * g + PF_BM - 1) / PF_BM;
         }
         p.tile_start[ns] = tiles;
         for (int i = ns + 1; i <= PF_MAX_SEQ; ++i) p.tile_start[i] = tiles;
+        for (int i = ns; i < PF_MAX_SEQ; ++i) p.env[i] = p.q_start[i] = p.n_q[i] = p.kv_len[i] = 0;
         dim3 grid(tiles, arena->n_kv_head);
         attn_prefill_kernel<<<grid, PF_THREADS, PF_SMEM, (cudaStream_t)stream>>>(map, p);
         rc = check_launch("attn_prefill_kernel");
         if (rc) return rc;
     }
     return SVLN_OK;
+}
+
+}  // namespace svln
+
+using namespace svln;
+
+extern "C" {
+
+int svln_attn_prefill(const svln_kv_arena* arena, int layer, const void* q, int n_q_head,
+                      const int32_t* seq_env_host, const int32_t* q_start_host, const int32_t* n_q_host,
+                      const int32_t* kv_len_host, int n_seq, float scale, void* workspace, size_t workspace_bytes,
+                      void* out, svln_stream_t stream) {
+    (void)workspace; (void)workspace_bytes;
+    return prefill_launch(arena, layer, q, n_q_head, seq_env_host, q_start_host, n_q_host, kv_len_host, nullptr, nullptr,
+                          nullptr, nullptr, n_seq, scale, out, stream, "svln_attn_prefill");
+}
+
+int svln_attn_prefill_dev(const svln_kv_arena* arena, int layer, const void* q, int n_q_head, const int32_t* seq_env,
+                          const int32_t* q_start, const int32_t* n_q, const int32_t* kv_len, const int32_t* n_q_host,
+                          int n_seq, float scale, void* out, svln_stream_t stream) {
+    SVLN_REQUIRE(seq_env, SVLN_ERR_INVALID, "svln_attn_prefill_dev: null seq_env");
+    return prefill_launch(arena, layer, q, n_q_head, nullptr, nullptr, n_q_host, nullptr, seq_env, q_start, n_q, kv_len,
+                          n_seq, scale, out, stream, "svln_attn_prefill_dev");
 }
 
 }  // extern "C"

@@ -141,6 +141,10 @@ class Qwen2Engine:
         self.launches = 0  # libsvln kernel launches (bench.py reports them as gpu_launches)
         self.prof = None   # bench.py: dict name -> [(start_event, end_event, algorithmic_work)] when profiling
         self._graphs: Dict[int, "_DecodeGraph"] = {}
+        self.use_prefill_graph = True
+        self._pgraphs: Dict[tuple, "_PrefillGraph"] = {}
+        self._pseen: Dict[tuple, int] = {}
+        self._prof_flops = 0.0
 
     # ------------------------------------------------------------------ small kernels
     def _rmsnorm(self, x: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
@@ -195,51 +199,70 @@ class Qwen2Engine:
     def forward(self, h: torch.Tensor, chunks: Sequence[Chunk], last_only: bool = True) -> torch.Tensor:
         """Packed forward of new tokens for several streams.  h [n_tok, D] bf16 input embeddings (consumed).
         Appends K/V to the arena, returns fp32 logits [n_chunks, vocab] of each chunk's last token (the
-        reference computes lm_head for every prefill row and discards all but the last)."""
-        dev = h.device
+        reference computes lm_head for every prefill row and discards all but the last).
+        Chunk shapes seen repeatedly (the steady-state turn) are replayed from a CUDA graph."""
         n_tok = h.shape[0]
         envs, poss = [], []
         for c in chunks:
             envs += [c.env] * c.n_q
             poss += list(range(c.kv_len - c.n_q, c.kv_len))
-            if c.kv_len > self.arena.max_len:
-                raise ValueError(f"stream {c.env}: {c.kv_len} tokens exceed the arena ({self.arena.max_len} rows)")
+            if c.kv_len > self.arena.max_len - 1:  # the last row is the CUDA-graph capture scratch row
+                raise ValueError(f"stream {c.env}: {c.kv_len} tokens exceed the arena ({self.arena.max_len - 1} usable rows)")
         assert len(envs) == n_tok
-        meta = torch.tensor([envs, poss], dtype=torch.int32).to(dev, non_blocking=True)
-        tok_env, tok_pos = meta[0], meta[1]
-        max_nq = max(c.n_q for c in chunks)
+        n_seq = len(chunks)
+        # one packed int32 upload: [tok_env | tok_pos | env | q_start | n_q | kv_len | last rows]
+        packed = torch.tensor(envs + poss + [c.env for c in chunks] + [c.q_start for c in chunks] + [c.n_q for c in chunks]
+                              + [c.kv_len for c in chunks] + [c.q_start + c.n_q - 1 for c in chunks], dtype=torch.int32)
+        key = tuple(c.n_q for c in chunks)
+        max_nq = max(key)
+        # algorithmic FLOPs of one prefill-attention launch (SURVEY §8d): Hq * 4 * d * n_q * (P + n_q / 2) per chunk
+        self._prof_flops = sum(self.cfg.num_attention_heads * 4 * self.cfg.head_dim * c.n_q * ((c.kv_len - c.n_q) + c.n_q / 2)
+                               for c in chunks)
+        graph = None
+        if self.use_prefill_graph and last_only and self.prof is None and max_nq > self.DECODE_MAX_NQ:
+            graph = self._pgraphs.get(key)
+            if graph is None:
+                self._pseen[key] = self._pseen.get(key, 0) + 1
+        if graph is not None:
+            logits = graph.run(h, packed)
+        else:
+            meta = packed.to(h.device, non_blocking=True)
+            logits = self._forward_core(h, meta, n_tok, n_seq, key, last_only)
+            if self.use_prefill_graph and last_only and self.prof is None and max_nq > self.DECODE_MAX_NQ \
+                    and self._pseen.get(key, 0) >= 2 and len(self._pgraphs) < 8:
+                self._pgraphs[key] = _PrefillGraph(self, key, n_tok)   # capture only; nothing executes
+        for c in chunks:
+            self.arena.lens[c.env] = c.kv_len
+        return logits
+
+    def _forward_core(self, h: torch.Tensor, meta: torch.Tensor, n_tok: int, n_seq: int, n_q_host, last_only: bool) -> torch.Tensor:
+        """Device-side part of `forward`: every descriptor lives in `meta` (device int32), so the launch
+        sequence is replayable from a CUDA graph for a fixed tuple of chunk lengths."""
+        tok_env, tok_pos = meta[:n_tok], meta[n_tok:2 * n_tok]
+        desc = meta[2 * n_tok:2 * n_tok + 4 * n_seq].view(4, n_seq)
+        rows = meta[2 * n_tok + 4 * n_seq:2 * n_tok + 5 * n_seq]
+        H = self.cfg.num_attention_heads
+        max_nq = max(n_q_host)
         if max_nq <= self.DECODE_MAX_NQ:
-            d = torch.tensor([[c.env for c in chunks], [c.q_start for c in chunks], [c.n_q for c in chunks],
-                              [c.kv_len for c in chunks]], dtype=torch.int32).to(dev, non_blocking=True)
-            max_kv = max(c.kv_len for c in chunks)
+            max_kv = self.arena.max_len
 
             def attn(li, q, out):
-                self.arena.attn_decode(li, q, self.cfg.num_attention_heads, d[0], d[1], d[2], d[3], max_nq, max_kv,
-                                       self.scale, out)
+                self.arena.attn_decode(li, q, H, desc[0], desc[1], desc[2], desc[3], max_nq, max_kv, self.scale, out)
                 self.launches += 2
         else:
-            se, qs = [c.env for c in chunks], [c.q_start for c in chunks]
-            nq, kl = [c.n_q for c in chunks], [c.kv_len for c in chunks]
-
-            # algorithmic FLOPs of one launch (SURVEY §8d): Hq * 4 * d * n_q * (P + n_q / 2) per chunk
-            flops = sum(self.cfg.num_attention_heads * 4 * self.cfg.head_dim * c.n_q * ((c.kv_len - c.n_q) + c.n_q / 2)
-                        for c in chunks)
-
             def attn(li, q, out):
                 if self.prof is not None:
                     s_ev, e_ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                     s_ev.record()
-                self.arena.attn_prefill(li, q, self.cfg.num_attention_heads, se, qs, nq, kl, self.scale, out)
+                self.arena.attn_prefill_dev(li, q, H, desc, n_q_host, self.scale, out)
                 if self.prof is not None:
                     e_ev.record()
-                    self.prof.setdefault("attn_prefill", []).append((s_ev, e_ev, flops))
+                    self.prof.setdefault("attn_prefill", []).append((s_ev, e_ev, self._prof_flops))
                 self.launches += 1
         h, pending = self._layers(h, tok_env, tok_pos, attn)
-        for c in chunks:
-            self.arena.lens[c.env] = c.kv_len
         if last_only:
-            rows = torch.tensor([c.q_start + c.n_q - 1 for c in chunks], dtype=torch.int64).to(dev, non_blocking=True)
-            h, pending = h.index_select(0, rows), pending.index_select(0, rows)
+            rows64 = rows.to(torch.int64)
+            h, pending = h.index_select(0, rows64), pending.index_select(0, rows64)
         x = self._add_rmsnorm(h, pending, self.w.final_norm)
         return (x @ self.w.lm_head.t()).float()
 
@@ -341,8 +364,8 @@ class _DecodeRunner:
     def step(self, tok: torch.Tensor) -> torch.Tensor:
         self.steps += 1
         for e in self.envs:
-            if self.eng.arena.lens[e] + self.steps > self.eng.arena.max_len:
-                raise ValueError(f"stream {e}: decode exceeds the arena ({self.eng.arena.max_len} rows)")
+            if self.eng.arena.lens[e] + self.steps > self.eng.arena.max_len - 1:
+                raise ValueError(f"stream {e}: decode exceeds the arena ({self.eng.arena.max_len - 1} usable rows)")
         if self.graph is not None:
             return self.graph.replay(tok)
         return self.eng.decode_step(tok, self.state)
@@ -358,23 +381,23 @@ class _DecodeGraph:
         self.state = _DecodeState(eng, [0] * B)
         self.tok_in = torch.zeros(B, dtype=torch.int64, device=eng.device)
         self.launches_per_replay = 0
-        # warm up on a side stream (allocator, cuBLAS workspaces), then capture.  Capture appends garbage
-        # rows past each stream's current length, which later real appends overwrite.
-        saved = [eng.arena.lens[0]]
-        self.state.kv_len.fill_(0)
+        # Warm up on a side stream (allocator, cuBLAS workspaces), then capture.  Both runs append one row per
+        # stream; they are pointed at the arena's LAST row, which live sequences never use (forward() and
+        # _DecodeRunner keep every stream at most max_len - 1 rows long), so no live cache row is touched.
+        scratch = eng.arena.max_len - 1
+        self.state.kv_len.fill_(scratch)
         s = torch.cuda.Stream(device=eng.device)
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
             eng.decode_step(self.tok_in, self.state)
         torch.cuda.current_stream().wait_stream(s)
-        self.state.kv_len.fill_(0)
+        self.state.kv_len.fill_(scratch)
         before = eng.launches
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.tok_out = eng.decode_step(self.tok_in, self.state)
         self.launches_per_replay = eng.launches - before
         eng.launches = before
-        eng.arena.lens[0] = saved[0]
 
     def bind(self, envs: List[int]) -> None:
         eng = self.eng
@@ -386,3 +409,32 @@ class _DecodeGraph:
         self.graph.replay()
         self.eng.launches += self.launches_per_replay
         return self.tok_out.clone()
+
+
+class _PrefillGraph:
+    """CUDA graph of one packed prefill forward for a fixed tuple of chunk lengths (the steady-state turn is
+    always 1 + n_text + 196 tokens): ~13 launches per layer collapse into one graph launch.  Cache lengths,
+    stream ids and positions are read from device memory, so the same graph serves every turn."""
+
+    def __init__(self, eng: Qwen2Engine, key: tuple, n_tok: int):
+        self.eng, self.key, self.n_tok = eng, key, n_tok
+        D = eng.cfg.hidden_size
+        n_seq = len(key)
+        self.h_in = torch.zeros(n_tok, D, dtype=torch.bfloat16, device=eng.device)
+        self.meta = torch.zeros(2 * n_tok + 5 * n_seq, dtype=torch.int32, device=eng.device)
+        self.meta_host = torch.zeros(2 * n_tok + 5 * n_seq, dtype=torch.int32).pin_memory()
+        before = eng.launches
+        self.graph = torch.cuda.CUDAGraph()
+        # the shapes were just run eagerly by forward() (cuBLAS / allocator are warm); capture executes nothing
+        with torch.cuda.graph(self.graph):
+            self.logits = eng._forward_core(self.h_in.clone(), self.meta, n_tok, n_seq, key, True)
+        self.launches_per_replay = eng.launches - before
+        eng.launches = before
+
+    def run(self, h: torch.Tensor, packed: torch.Tensor) -> torch.Tensor:
+        self.meta_host.copy_(packed)
+        self.meta.copy_(self.meta_host, non_blocking=True)
+        self.h_in.copy_(h)
+        self.graph.replay()
+        self.eng.launches += self.launches_per_replay
+        return self.logits

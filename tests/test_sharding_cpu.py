@@ -1,0 +1,121 @@
+"""CPU tests of the N>1 host logic: episode sharding and the final metric gather over gloo (world_size 2),
+the C-ABI export list, and host-side helpers."""
+import os
+import re
+from pathlib import Path
+
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def test_shard_episodes_matches_reference_rule():
+    from streamvln_b200.scheduler import shard_episodes
+
+    eps = list(range(11))
+    parts = [shard_episodes(eps, r, 4) for r in range(4)]
+    assert parts == [[0, 4, 8], [1, 5, 9], [2, 6, 10], [3, 7]]
+    assert sorted(sum(parts, [])) == eps
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch.distributed as dist
+    from streamvln_b200.scheduler import EpisodeResult, gather_results, hash_actions, shard_episodes
+
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    mine = shard_episodes(list(range(7)), rank, world)
+    local = [EpisodeResult(e, 40 + e, 10 + e, hash_actions([e % 4, 1, 2, 3] * (e + 1)), 0.5 * e) for e in mine]
+    allr = gather_results(local)
+    dist.barrier()
+    q.put((rank, [(r.episode_id, r.steps, r.turns, r.action_hash, r.seconds) for r in allr]))
+    dist.destroy_process_group()
+
+
+def test_gather_results_gloo_world2():
+    from streamvln_b200.scheduler import hash_actions
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    want = [(e, 40 + e, 10 + e, hash_actions([e % 4, 1, 2, 3] * (e + 1)), 0.5 * e) for e in range(7)]
+    assert got[0] == want and got[1] == want     # uneven shards (4 + 3 episodes), every rank sees all results
+
+
+def test_cabi_exports_every_declared_symbol(svln_lib):
+    """The shared library loads without a GPU and exports exactly what include/svln.h declares."""
+    from streamvln_b200 import _lib
+
+    header = (ROOT / "include" / "svln.h").read_text()
+    declared = set(re.findall(r"\b(svln_[a-z0-9_]+)\s*\(", header))
+    declared -= {"svln_stream_t"}
+    assert declared == set(_lib.PROTOTYPES), declared ^ set(_lib.PROTOTYPES)
+    for name in declared:
+        assert hasattr(svln_lib, name), name
+    assert svln_lib.svln_version() == 100
+    # pure host-side size queries work without a device
+    assert svln_lib.svln_kv_arena_bytes(1, 28, 4, 128, 4096) == 57344 * 4096
+    assert svln_lib.svln_kv_arena_bytes(0, 28, 4, 128, 4096) == 0
+    assert svln_lib.svln_prune_workspace_bytes(6272, 1, 6272) > 0
+    assert svln_lib.svln_attn_workspace_bytes(64, 28, 128, 4096) > 0
+    assert svln_lib.svln_voxel_prune_host_staging_bytes(1, 32, 384, 384, 14, 3584) > 32 * 196 * 3584 * 4
+
+
+def test_product_never_imports_oracle():
+    """The product path must not route through the oracle (or any CPU fallback)."""
+    for f in (ROOT / "streamvln_b200").rglob("*.py"):
+        src = f.read_text()
+        assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f
+    for f in (ROOT / "streamvln_b200" / "csrc").glob("*"):
+        assert "oracle" not in f.read_text().replace("oracle/voxel_oracle.c", "").replace("CPU oracle", "").replace("oracle (", ""), f
+
+
+def test_missing_library_fails_loudly(tmp_path, monkeypatch):
+    from streamvln_b200 import _lib
+
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", tmp_path / "nope.so")
+    with pytest.raises(ImportError):
+        _lib.load()
+
+
+def test_stub_tokenizer_and_prompt_layout():
+    """Prompt layout of SURVEY §3.1b with the offline tokenizer: system block only on a window's first turn, the
+    empty assistant block is rendered closed, <image>/<memory> become -200/-300."""
+    from streamvln_b200.tokenizer import StubQwenTokenizer
+
+    tok = StubQwenTokenizer(152064)
+    tok.add_tokens(["<image>"], special_tokens=True)
+    tok.add_tokens(["<memory>"], special_tokens=True)
+    ids = tok.apply_chat_template([{"role": "user", "content": "you can see <image>."}, {"role": "assistant", "content": ""}])
+    im_s, im_e = tok.additional_special_tokens_ids
+    assert ids[0] == im_s and ids.count(im_s) == 2 and ids.count(im_e) == 2 and ids[-1] == 198
+    assert ids.count(tok.convert_tokens_to_ids("<image>")) == 1
+    assert tok.batch_decode([[im_s, im_e, 198]])[0] == "<|im_start|><|im_end|>\n"
+    assert tok.encode("walk to the door") == tok.encode("walk  to the\tdoor")
+
+
+def test_synth_geometry_conventions():
+    """Intrinsics and pose conventions of streamvln_eval.py:137-185."""
+    import numpy as np
+    from streamvln_b200 import synth
+
+    K = synth.intrinsic_matrix()
+    assert abs(K[0, 0] - 232.9) < 0.1 and abs(K[1, 1] - 310.6) < 0.1
+    assert abs(K[0, 2] - 191.7) < 0.01 and abs(K[1, 2] - 191.6) < 0.01
+    P = synth.pose_matrix(1.0, 2.0, 0.0)
+    # camera z (forward) maps to episodic +x; camera x (right) maps to episodic -y; camera y (down) to -z
+    assert np.allclose(P[:3, :3] @ np.array([0, 0, 1.0]), [1, 0, 0])
+    assert np.allclose(P[:3, :3] @ np.array([1.0, 0, 0]), [0, -1, 0])
+    assert np.allclose(P[:3, 3], [1.0, -2.0, 1.25])
+    a, poses = synth.action_walk(50, np.random.default_rng(0))
+    assert set(a.tolist()) <= {1, 2, 3} and poses.shape == (50, 4, 4)
