@@ -142,6 +142,99 @@ def timed(agent, model, n_turns, frames_host, frames_dev, resident, dist, device
     return ms, model.engine.launches - l0, h2d, d2h
 
 
+def main_batched(a):
+    """BASELINE.json configs[2]: E concurrent synthetic episodes sharded across the GPUs of one box (E/N per GPU,
+    total fixed -> strong scaling); every model step packs the turns of all local streams into one forward."""
+    import numpy as np
+    import torch
+    from streamvln_b200 import build as svln_build
+    from streamvln_b200.model import StreamVLNConfig, StreamVLNForCausalLM
+    from streamvln_b200.scheduler import BatchedEvaluator
+    from streamvln_b200.synth import intrinsic_matrix
+    from streamvln_b200.tokenizer import StubQwenTokenizer
+
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    device = torch.device(f"cuda:{local}")
+    torch.cuda.set_device(device)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+
+        dist_mod.init_process_group("nccl", device_id=device)
+        dist = dist_mod
+    svln_build.build()
+    E = a.episodes // world
+    cfg = StreamVLNConfig(mode=a.mode)
+    model = StreamVLNForCausalLM(cfg, n_env=E, device=device, seed=0)
+    args = SimpleNamespace(num_frames=32, num_future_steps=ENV_STEPS_PER_TURN, num_history=8, max_new_tokens=N_GEN)
+    ev = BatchedEvaluator(model, lambda: StubQwenTokenizer(cfg.llm.vocab_size), E, args, {"camera_intrinsic": intrinsic_matrix()})
+    rng = np.random.default_rng(99 + rank)
+    frames_host = rng.integers(0, 255, size=(16, 480, 640, 3), dtype=np.uint8)
+    from PIL import Image
+
+    proc = ev.agents[0].image_processor
+    frames_dev = torch.stack([proc.preprocess(images=Image.fromarray(f), return_tensors="pt")["pixel_values"][0]
+                              for f in frames_host]).to(device)
+    live = list(range(E))
+    instr = {i: INSTRUCTION for i in live}
+
+    def turns(n, resident):
+        for _ in range(n):
+            for k in range(ENV_STEPS_PER_TURN):
+                s = ev.agents[0].step_id
+                if resident:
+                    ev.step_all(live, None, instr, k == 0, None, {i: frames_dev[(s + i) % 16] for i in live} if k == 0 else None)
+                else:
+                    ev.step_all(live, {i: frames_host[(s + i) % 16] for i in live}, instr, k == 0)
+
+    def run(n, resident):
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(device)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = model.engine.launches
+        e0.record()
+        turns(n, resident)
+        e1.record()
+        torch.cuda.synchronize(device)
+        ms = e0.elapsed_time(e1)
+        if dist is not None:
+            dist.barrier()
+            t = torch.tensor([ms], device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, model.engine.launches - l0
+
+    K, W = a.steps, a.warmup
+    turns(W, True)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms, launches = run(K, True)
+    clocks = sampler.stop() if rank == 0 else None
+    for i in live:
+        ev.reset_stream(i)
+    turns(min(W, 3), False)
+    ms_e2e, _ = run(K, False)
+    total = E * world * K * ENV_STEPS_PER_TURN
+    out = {"metric": METRIC, "value": round(total / (ms / 1e3), 2), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+           "ms_per_step": round(ms / K, 3), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16",
+           "data": "synthetic",
+           "config": {"workload": f"configs[2]: {a.episodes} concurrent synthetic R2R-shaped episodes sharded across {world} GPU(s) "
+                                  f"({E} per GPU), LLaVA-Video-7B-Qwen2 shapes, num_history=8, n_gen=5, bf16, random-init weights",
+                      "mode": a.mode, "env_steps_per_step": ENV_STEPS_PER_TURN, "episodes_per_gpu": E,
+                      "step_definition": "1 bench step = 1 packed model turn of every stream = 4 env steps per stream"},
+           "e2e": {"value": round(total / (ms_e2e / 1e3), 2), "unit": UNIT, "ms_per_step": round(ms_e2e / K, 3),
+                   "h2d_bytes_per_step": int(E * 3 * 384 * 384 * 4), "d2h_bytes_per_step": int(E * N_GEN * 8)},
+           "gpu_launches": int(launches), "clocks": clocks}
+    if rank == 0:
+        print(json.dumps(out), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main_ours(a):
     import numpy as np
     import torch
@@ -294,12 +387,15 @@ def main():
     ap.add_argument("--warmup", type=int, default=8)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default="reference", choices=["reference", "slowfast"])
+    ap.add_argument("--episodes", type=int, default=1, help="total concurrent episodes (>1: configs[2], sharded across GPUs)")
     ap.add_argument("--no-micro", action="store_true", help="skip the per-kernel microbenchmarks")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3)
     if a.impl == "reference":
         main_reference(a)
+    elif a.episodes > 1:
+        main_batched(a)
     else:
         main_ours(a)
 

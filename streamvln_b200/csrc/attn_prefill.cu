@@ -7,12 +7,14 @@
 // (query token, head-in-GQA-group) pairs R = tq * g + hg, so the g query heads that share a KV
 // head reuse every K/V tile (GQA packing) and causal limits are monotone in R.
 //
-//   warps 0-3 : softmax.  Thread i of warp w owns TMEM lane 32w+i = tile row 32w+i, so row max /
-//               row sum need no shuffles.  Loads S with tcgen05.ld, writes P (bf16) to swizzled
-//               smem, rescales O in TMEM lazily (only when the running max grew by > 2^8).
-//   warp 4    : one elected thread issues tcgen05.mma: S = Q K^T (SS, K-major x K-major) into a
+//   warps 0-7 : softmax.  Warps w and w+4 share TMEM lanes 32(w%4)..+31 (= tile rows) and take 64 columns
+//               each, so every SM sub-partition runs two softmax warps (MUFU / FMA latency of one hides
+//               behind the other) and a row's max / sum needs one 2-thread exchange through shared
+//               memory (64-thread named barrier), no shuffles.  Loads S with tcgen05.ld, writes P (bf16)
+//               to swizzled smem, rescales O in TMEM lazily (only when the running max grew by > 2^8).
+//   warp 8    : one elected thread issues tcgen05.mma: S = Q K^T (SS, K-major x K-major) into a
 //               double-buffered S in TMEM, and O += P V (SS, K-major x MN-major).
-//   warp 5    : one elected thread issues TMA loads of K and V tiles (128 keys x 128 dims, two
+//   warp 9    : one elected thread issues TMA loads of K and V tiles (128 keys x 128 dims, two
 //               64-column SWIZZLE_128B panels each) into 2-stage rings.
 // TMEM: S0 cols [0,128), S1 [128,256), O [256,384) of a 512-column allocation.
 #include <cuda.h>
@@ -27,7 +29,8 @@ constexpr int PF_BN = 128;   // keys per KV tile
 constexpr int PF_HD = 128;   // head_dim
 constexpr int PF_PANEL = 128 * 128;            // bytes of one [128 rows][64 elem] SW128 panel
 constexpr int PF_TILE = 2 * PF_PANEL;          // 32 KB: a [128][128] bf16 tile = two panels
-constexpr int PF_THREADS = 192;
+constexpr int PF_SOFTMAX_WARPS = 8;  // two threads per tile row (64 columns each): 2 warps per SM sub-partition
+constexpr int PF_THREADS = (PF_SOFTMAX_WARPS + 2) * 32;
 constexpr int PF_MAX_SEQ = 64;
 
 // shared memory map (dynamic, 1024-aligned)
@@ -36,7 +39,8 @@ constexpr int SM_K = SM_Q + PF_TILE;           // 2 stages
 constexpr int SM_V = SM_K + 2 * PF_TILE;       // 2 stages
 constexpr int SM_P = SM_V + 2 * PF_TILE;
 constexpr int SM_BAR = SM_P + PF_TILE;         // barriers + tmem pointer
-constexpr int PF_SMEM = SM_BAR + 256 + 1024;   // + alignment slack
+constexpr int SM_XCH = SM_BAR + 256;           // float [2 tiles][2 halves][128 rows] row-max exchange
+constexpr int PF_SMEM = SM_XCH + 3 * 2 * 128 * 4 + 1024;   // (+ one [2][128] block for the row-sum exchange) + alignment slack
 
 enum { BAR_K_FULL = 0, BAR_K_EMPTY = 2, BAR_V_FULL = 4, BAR_V_EMPTY = 6, BAR_S_FULL = 8, BAR_S_EMPTY = 10,
        BAR_P_FULL = 12, BAR_PV_DONE = 13, BAR_COUNT = 14 };
@@ -115,6 +119,18 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// two fp32 -> packed bf16x2 (lo in bits [0,16)), round-to-nearest-even, one instruction
+__device__ __forceinline__ uint32_t pack2_bf16(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+
 // Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): SWIZZLE_128B, version 1.
 //   bits [0,14) start>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version=1 | [61,64) layout=2
 __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -173,8 +189,8 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap kv_map, const __grid_con
         mbar_init(BAR(BAR_V_FULL), 1); mbar_init(BAR(BAR_V_FULL + 1), 1);
         mbar_init(BAR(BAR_V_EMPTY), 1); mbar_init(BAR(BAR_V_EMPTY + 1), 1);
         mbar_init(BAR(BAR_S_FULL), 1); mbar_init(BAR(BAR_S_FULL + 1), 1);
-        mbar_init(BAR(BAR_S_EMPTY), 128); mbar_init(BAR(BAR_S_EMPTY + 1), 128);
-        mbar_init(BAR(BAR_P_FULL), 128);
+        mbar_init(BAR(BAR_S_EMPTY), PF_SOFTMAX_WARPS * 32); mbar_init(BAR(BAR_S_EMPTY + 1), PF_SOFTMAX_WARPS * 32);
+        mbar_init(BAR(BAR_P_FULL), PF_SOFTMAX_WARPS * 32);
         mbar_init(BAR(BAR_PV_DONE), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -182,22 +198,23 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap kv_map, const __grid_con
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(s2u(tmem_ptr_smem)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    // Q tile -> swizzled smem (generic proxy), rows past the end are zero
-    if (tid < PF_BM) {
-        const int r = tid;
+    // Q tile -> swizzled smem (generic proxy), rows past the end are zero.  Thread mapping = softmax mapping:
+    // row 32*(warp%4)+lane, column half warp/4 (eight 16-byte chunks).
+    if (warp < PF_SOFTMAX_WARPS) {
+        const int r = (warp & 3) * 32 + lane, half = warp >> 2;
         const int R = row0 + r;
-        int4 v[16];
+        int4 v[8];
         if (r < rows_here) {
             const int tq = R / g, hg = R - tq * g;
-            const int4* src = reinterpret_cast<const int4*>(p.q + ((int64_t)(qs + tq) * p.n_q_head + kvh * g + hg) * PF_HD);
+            const int4* src = reinterpret_cast<const int4*>(p.q + ((int64_t)(qs + tq) * p.n_q_head + kvh * g + hg) * PF_HD) + half * 8;
 #pragma unroll
-            for (int c = 0; c < 16; ++c) v[c] = __ldg(src + c);
+            for (int c = 0; c < 8; ++c) v[c] = __ldg(src + c);
         } else {
 #pragma unroll
-            for (int c = 0; c < 16; ++c) v[c] = make_int4(0, 0, 0, 0);
+            for (int c = 0; c < 8; ++c) v[c] = make_int4(0, 0, 0, 0);
         }
 #pragma unroll
-        for (int c = 0; c < 16; ++c) *reinterpret_cast<int4*>(smem + SM_Q + kmajor_off(r, c)) = v[c];
+        for (int c = 0; c < 8; ++c) *reinterpret_cast<int4*>(smem + SM_Q + kmajor_off(r, half * 8 + c)) = v[c];
     }
     fence_async_smem();  // make the generic-proxy smem writes visible to the async proxy (MMA)
     tc_fence_before();
@@ -206,7 +223,7 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap kv_map, const __grid_con
     const uint32_t tmem_base = *tmem_ptr_smem;
     const uint32_t TM_S0 = tmem_base, TM_O = tmem_base + 256;
 
-    if (warp == 5) {
+    if (warp == PF_SOFTMAX_WARPS + 1) {
         // ------------------------------------------------------------ TMA producer
         if (lane == 0) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(&kv_map) : "memory");
@@ -223,7 +240,7 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap kv_map, const __grid_con
                 tma_load_3d(sbase + SM_V + s * PF_TILE + PF_PANEL, &kv_map, BAR(BAR_V_FULL + s), 64, key0, plane_v);
             }
         }
-    } else if (warp == 4) {
+    } else if (warp == PF_SOFTMAX_WARPS) {
         // ------------------------------------------------------------ MMA issuer
         if (lane == 0) {
             constexpr uint32_t IDESC_QK = umma_idesc(0);  // A, B K-major
@@ -271,39 +288,49 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap kv_map, const __grid_con
             }
         }
     } else {
-        // ------------------------------------------------------------ softmax warps (rows)
-        const int r = tid;                       // tile row == TMEM lane
+        // ------------------------------------------------------------ softmax warps
+        const int r = (warp & 3) * 32 + lane;    // tile row == TMEM lane
+        const int half = warp >> 2;              // columns [64*half, 64*half + 64)
         const int R = row0 + r;
         const bool row_valid = r < rows_here;
         const int tq = row_valid ? R / g : 0;
         const int hg = row_valid ? R - tq * g : 0;
         const int lim = row_valid ? len - nq + tq + 1 : 0;   // keys < lim are visible
-        const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
-        float m_used = -INFINITY;   // running max in scaled (log2) units
-        float l_sum = 0.f;
+        const uint32_t lane_addr = ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(half * 64);
+        float* xch = reinterpret_cast<float*>(smem + SM_XCH);  // [tile parity][half][row]
+        const int pair_bar = 1 + (warp & 3);                   // named barrier shared by warps w and w+4
+        float m_used = -INFINITY;   // running reference max in scaled (log2) units; identical in both halves
+        float l_sum = 0.f;          // this thread's half of the row sum
         for (int j = 0; j < n_tiles; ++j) {
             const int s = j & 1, u = j >> 1;
             mbar_wait(BAR(BAR_S_FULL + s), u & 1);
             tc_fence_after();
-            uint32_t sv[4][32];
+            uint32_t sv[2][32];
 #pragma unroll
-            for (int c = 0; c < 4; ++c) tmem_ld32(TM_S0 + s * 128 + lane_addr + c * 32, sv[c]);
+            for (int c = 0; c < 2; ++c) tmem_ld32(TM_S0 + s * 128 + lane_addr + c * 32, sv[c]);
             tmem_wait_ld();
             tc_fence_before();
             mbar_arrive(BAR(BAR_S_EMPTY + s));
-            // scale, mask, row max
-            const int key0 = j * PF_BN;
-            const bool need_mask = key0 + PF_BN > lim;
+            // mask + row max on the raw scores (scale > 0 commutes with max)
+            const int key0 = j * PF_BN + half * 64;
             float mx = -INFINITY;
+            if (key0 + 64 > lim) {
 #pragma unroll
-            for (int c = 0; c < 4; ++c)
+                for (int c = 0; c < 2; ++c)
 #pragma unroll
-                for (int e = 0; e < 32; ++e) {
-                    float x = __uint_as_float(sv[c][e]) * p.scale_log2;
-                    if (need_mask && key0 + c * 32 + e >= lim) x = -INFINITY;
-                    sv[c][e] = __float_as_uint(x);
-                    mx = fmaxf(mx, x);
-                }
+                    for (int e = 0; e < 32; ++e) {
+                        if (key0 + c * 32 + e >= lim) sv[c][e] = 0xFF800000u;  // -inf
+                        mx = fmaxf(mx, __uint_as_float(sv[c][e]));
+                    }
+            } else {
+#pragma unroll
+                for (int c = 0; c < 2; ++c)
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) mx = fmaxf(mx, __uint_as_float(sv[c][e]));
+            }
+            xch[(s * 2 + half) * 128 + r] = mx;
+            asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+            mx = fmaxf(mx, xch[(s * 2 + (half ^ 1)) * 128 + r]) * p.scale_log2;
             // lazy rescale: only move the reference max when it grew by more than 8 (factor 256)
             float alpha = 1.f;
             bool rescale = false;
@@ -312,14 +339,14 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap kv_map, const __grid_con
                 m_used = mx;
                 rescale = j > 0;
             }
-            const float m_sub = m_used == -INFINITY ? 0.f : m_used;
+            const float neg_m = m_used == -INFINITY ? 0.f : -m_used;
             // P buffer and O are free once PV(j-1) has completed
             if (j > 0) mbar_wait(BAR(BAR_PV_DONE), (j - 1) & 1);
             tc_fence_after();
+            l_sum *= alpha;
             if (__any_sync(0xffffffffu, rescale)) {
-                l_sum *= alpha;
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
+                for (int c = 0; c < 2; ++c) {
                     uint32_t ov[32];
                     tmem_ld32(TM_O + lane_addr + c * 32, ov);
                     tmem_wait_ld();
@@ -328,24 +355,22 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap kv_map, const __grid_con
                     tmem_st32(TM_O + lane_addr + c * 32, ov);
                 }
                 tmem_wait_st();
-            } else {
-                l_sum *= alpha;  // alpha == 1 unless this is the first tile
             }
-            // P = exp2(S - m), row sum in fp32, P rounded to bf16 into swizzled smem
+            // P = exp2(S * scale - m): one FFMA + one MUFU per element; row sum in fp32; bf16 into swizzled smem
             float psum = 0.f;
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
+            for (int c = 0; c < 2; ++c) {
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {  // 8 keys = one 16-byte chunk
                     uint32_t w[4];
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
-                        const float p0 = exp2f(__uint_as_float(sv[c][q * 8 + 2 * e]) - m_sub);
-                        const float p1 = exp2f(__uint_as_float(sv[c][q * 8 + 2 * e + 1]) - m_sub);
+                        const float p0 = ex2_approx(fmaf(__uint_as_float(sv[c][q * 8 + 2 * e]), p.scale_log2, neg_m));
+                        const float p1 = ex2_approx(fmaf(__uint_as_float(sv[c][q * 8 + 2 * e + 1]), p.scale_log2, neg_m));
                         psum += p0 + p1;
-                        w[e] = f32_to_bf16_bits(p0) | (f32_to_bf16_bits(p1) << 16);
+                        w[e] = pack2_bf16(p0, p1);
                     }
-                    *reinterpret_cast<int4*>(smem + SM_P + kmajor_off(r, c * 4 + q)) = make_int4(w[0], w[1], w[2], w[3]);
+                    *reinterpret_cast<int4*>(smem + SM_P + kmajor_off(r, half * 8 + c * 4 + q)) = make_int4(w[0], w[1], w[2], w[3]);
                 }
             }
             l_sum += psum;
@@ -353,13 +378,16 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap kv_map, const __grid_con
             tc_fence_before();
             mbar_arrive(BAR(BAR_P_FULL));
         }
-        // epilogue: O / l -> bf16 -> global
+        // epilogue: O / l -> bf16 -> global (this thread: 64 dims of its row)
+        xch[(4 + half) * 128 + r] = l_sum;   // separate block: the partner may still be reading the last row max
+        asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+        const float l_tot = l_sum + xch[(4 + (half ^ 1)) * 128 + r];
         mbar_wait(BAR(BAR_PV_DONE), (n_tiles - 1) & 1);
         tc_fence_after();
-        const float inv_l = l_sum > 0.f ? 1.0f / l_sum : 0.f;
-        __nv_bfloat16* orow = p.out + ((int64_t)(qs + tq) * p.n_q_head + kvh * g + hg) * PF_HD;
+        const float inv_l = l_tot > 0.f ? 1.0f / l_tot : 0.f;
+        __nv_bfloat16* orow = p.out + ((int64_t)(qs + tq) * p.n_q_head + kvh * g + hg) * PF_HD + half * 64;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < 2; ++c) {
             uint32_t ov[32];
             tmem_ld32(TM_O + lane_addr + c * 32, ov);
             tmem_wait_ld();
@@ -369,8 +397,7 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap kv_map, const __grid_con
                     uint32_t w[4];
 #pragma unroll
                     for (int e = 0; e < 4; ++e)
-                        w[e] = f32_to_bf16_bits(__uint_as_float(ov[q * 8 + 2 * e]) * inv_l) |
-                               (f32_to_bf16_bits(__uint_as_float(ov[q * 8 + 2 * e + 1]) * inv_l) << 16);
+                        w[e] = pack2_bf16(__uint_as_float(ov[q * 8 + 2 * e]) * inv_l, __uint_as_float(ov[q * 8 + 2 * e + 1]) * inv_l);
                     *reinterpret_cast<int4*>(orow + c * 32 + q * 8) = make_int4(w[0], w[1], w[2], w[3]);
                 }
             }

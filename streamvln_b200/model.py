@@ -168,6 +168,27 @@ class StreamVLNForCausalLM:
                 cache[frame_ids[i]] = new[j]
         return torch.stack([cache[f] for f in frame_ids])
 
+    def _prefetch_features(self, requests: Sequence[Dict[str, Any]], max_batch: int = 16) -> None:
+        """Encode, in as few SigLIP batches as possible, every frame of this batch of turns that is not in the
+        per-stream feature cache yet (requests that carry `frame_ids`)."""
+        todo = []
+        for r in requests:
+            fids, images = r.get("frame_ids"), r.get("images")
+            if fids is None or images is None:
+                continue
+            env = r.get("env_id", 0) or 0
+            cache = self.feat_cache[env]
+            for i, f in enumerate(fids):
+                if f not in cache and all(not (e == env and g == f) for e, g, _ in todo):
+                    todo.append((env, f, images[0, i]))
+        if len(todo) <= 1:
+            return  # a single frame goes through the (CUDA-graphed) per-request path
+        for b0 in range(0, len(todo), max_batch):
+            part = todo[b0:b0 + max_batch]
+            feats = self.vision(torch.stack([x[2].to(self.device) for x in part]))
+            for (env, f, _), ft in zip(part, feats):
+                self.feat_cache[env][f] = ft
+
     # ------------------------------------------------------------------ embed splice
     def splice(self, input_ids: Sequence[int], image_features: torch.Tensor, memory_features: Optional[torch.Tensor]) -> torch.Tensor:
         """prepare_inputs_labels_for_multimodal (stream_video_vln.py:144-291), inference path, one sample:
@@ -225,6 +246,7 @@ class StreamVLNForCausalLM:
         """Several streams' turns in one packed forward (one request per env_id; same kwargs as `generate`).
         This is what lets 64 concurrent episodes share every GEMM."""
         tails, envs, max_new = [], [], []
+        self._prefetch_features(requests)
         for r in requests:
             r = dict(r)
             if "inputs_embeds" in r:

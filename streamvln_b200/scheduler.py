@@ -81,6 +81,7 @@ class BatchedEvaluator:
         self.agents = [VLNEvaluator(sim_sensors_config, model=model, tokenizer=make_tokenizer(), args=args)
                        for _ in range(n_streams)]
         self.n = n_streams
+        self._pool = None
 
     def reset_stream(self, i: int):
         self.agents[i]._init_state()
@@ -90,6 +91,18 @@ class BatchedEvaluator:
                  geom: Optional[Dict[int, dict]] = None, preprocessed: Optional[Dict[int, torch.Tensor]] = None):
         """One env step for every live stream.  Returns {stream: action list} on a model step, else {}."""
         reqs, who = [], []
+        if run_model and frames and preprocessed is None and len(live) > 1:
+            # host uint8 frames: run the PIL image processor of all streams on a thread pool (PIL drops the GIL)
+            from concurrent.futures import ThreadPoolExecutor
+            from PIL import Image
+            import os
+
+            if self._pool is None:
+                self._pool = ThreadPoolExecutor(max_workers=min(32, os.cpu_count() or 4))
+            proc = self.agents[0].image_processor
+            futs = {i: self._pool.submit(lambda f: proc.preprocess(images=Image.fromarray(f).convert("RGB"),
+                                                                   return_tensors="pt")["pixel_values"][0], frames[i]) for i in live}
+            preprocessed = {i: f.result() for i, f in futs.items()}
         for i in live:
             g = geom[i] if geom else {}
             req = self.agents[i].prepare(i, frames.get(i) if frames else None, instructions[i], run_model, g.get("depth"),
