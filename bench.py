@@ -128,10 +128,16 @@ def timed(agent, model, n_turns, frames_host, frames_dev, resident, dist, device
     torch.cuda.synchronize(device)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     l0 = model.engine.launches
+    rng_on = os.environ.get("SVLN_NCU_RANGE") == ("resident" if resident else "e2e")
+    if rng_on:  # `ncu --profile-from-start off`: profile exactly this timed region
+        torch.cuda.profiler.start()
     e0.record()
     h2d, d2h = run_turns(agent, n_turns, frames_host, frames_dev, resident, geom)
     e1.record()
     torch.cuda.synchronize(device)
+    if rng_on:
+        torch.cuda.profiler.stop()
+        os.environ["SVLN_NCU_RANGE"] = "done"
     if dist is not None:
         dist.barrier()
     ms = e0.elapsed_time(e1)

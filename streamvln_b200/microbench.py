@@ -14,6 +14,10 @@ KV_BYTES_PER_TOKEN = 2 * 28 * 4 * 128 * 2  # 57 344 B: K+V, 28 layers, 4 kv head
 
 def _time(fn: Callable[[], None], iters: int = 10, warmup: int = 3) -> float:
     """average milliseconds per call (CUDA events on the current stream)"""
+    import os
+
+    if os.environ.get("SVLN_MICRO_ITERS"):  # profiling runs: launch each kernel only a couple of times
+        iters, warmup = int(os.environ["SVLN_MICRO_ITERS"]), 1
     for _ in range(warmup):
         fn()
     torch.cuda.synchronize()

@@ -9,6 +9,7 @@ packed into one [n_tok, hidden] batch so every GEMM serves all concurrent episod
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Sequence
 
@@ -141,7 +142,9 @@ class Qwen2Engine:
         self.launches = 0  # libsvln kernel launches (bench.py reports them as gpu_launches)
         self.prof = None   # bench.py: dict name -> [(start_event, end_event, algorithmic_work)] when profiling
         self._graphs: Dict[int, "_DecodeGraph"] = {}
-        self.use_prefill_graph = True
+        # SVLN_NO_GRAPH=1 launches everything eagerly (ncu cannot profile kernels issued during stream capture)
+        self.use_graphs = os.environ.get("SVLN_NO_GRAPH", "0") != "1"
+        self.use_prefill_graph = self.use_graphs
         self._pgraphs: Dict[tuple, "_PrefillGraph"] = {}
         self._pseen: Dict[tuple, int] = {}
         self._prof_flops = 0.0
@@ -284,7 +287,7 @@ class Qwen2Engine:
         tok = self.argmax(logits)
         out = [tok]
         if max_new_tokens > 1:
-            runner = self._decode_runner(envs, use_graph)
+            runner = self._decode_runner(envs, use_graph and self.use_graphs)
             alive = None
             for _ in range(max_new_tokens - 1):
                 if eos_token_id is not None:

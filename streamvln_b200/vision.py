@@ -11,6 +11,7 @@ its num_history frames.
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass
 from typing import Dict, Optional
 
@@ -96,7 +97,7 @@ class VisionFrontEnd(torch.nn.Module):
         self.proj_w1, self.proj_b1 = p(cfg.out_dim, D), p(cfg.out_dim)
         self.proj_w2, self.proj_b2 = p(cfg.out_dim, cfg.out_dim), p(cfg.out_dim)
         self.to(device)
-        self.use_graph = True
+        self.use_graph = os.environ.get("SVLN_NO_GRAPH", "0") != "1"
         self._graphs: Dict[int, dict] = {}
         self._seen: Dict[int, int] = {}
 
