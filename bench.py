@@ -35,6 +35,7 @@ METRIC = "streaming_nav_steps_per_sec"
 UNIT = "env_steps/s"
 ENV_STEPS_PER_TURN = 4
 N_GEN = 5
+PRIME_TURNS = 17
 INSTRUCTION = ("walk down the hallway past the kitchen turn left at the sofa go through the second door on the right "
                "and wait by the window next to the wooden table in the corner of the bedroom then stop near the bed "
                "facing the large mirror on the wall")  # 48 words ~ the 40 fixed token ids of SURVEY §8d
@@ -213,6 +214,9 @@ def main_batched(a):
         return ms, model.engine.launches - l0
 
     K, W = a.steps, a.warmup
+    turns(PRIME_TURNS, True)   # graph priming (see main_ours)
+    for i in live:
+        ev.reset_stream(i)
     turns(W, True)
     sampler = ClockSampler(local)
     if rank == 0:
@@ -276,6 +280,10 @@ def main_ours(a):
     frames_dev = torch.stack([proc.preprocess(images=Image.fromarray(f), return_tensors="pt")["pixel_values"][0]
                               for f in frames_host]).to(device)
     K, W = a.steps, a.warmup
+    # ---- priming (initialisation, like building the model): one throw-away episode of two windows + one turn, so
+    #      every CUDA graph the steady state replays (vision, steady turn, window-start turn, decode) is captured
+    #      before any warm-up or timed step.  Graphs are captured on the second sighting of a shape.
+    run_turns(agent, PRIME_TURNS, frames_host, frames_dev, True, geom)
     # ---- device-resident arm
     agent.reset_memory()
     run_turns(agent, W, frames_host, frames_dev, True, geom)

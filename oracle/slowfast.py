@@ -47,7 +47,8 @@ class SlowFastOracle:
         return glue.splice(ids, table, feats.to(table.dtype), None)
 
     @torch.no_grad()
-    def generate(self, ids: List[int], feats: torch.Tensor, depth, pose, intr, t: int, max_new_tokens: int):
+    def generate(self, ids: List[int], feats: torch.Tensor, depth, pose, intr, t: int, max_new_tokens: int,
+                 force_tokens: Optional[Sequence[int]] = None):
         """ids: the caller's input ids (first turn: full prompt with one <memory>; later: previous output ids +
         the new turn).  feats [1,196,D] pooled features of the current frame; depth [384,384], pose/intr [4,4]."""
         keys = ov.c_voxel_keys(np.asarray(depth, np.float32)[None], np.asarray(pose, np.float32)[None],
@@ -70,12 +71,17 @@ class SlowFastOracle:
         out = self.lm(inputs_embeds=emb[None], past_key_values=self.cache, position_ids=pos, use_cache=True)
         logits = out.logits[:, -1].float()
         self.first_logits.append(logits[0].clone())
-        tok = logits.argmax(-1)
+        self.step_logits = [logits[0].clone()]
+        # teacher forcing (parity tests): follow the implementation under test through near-ties
+        pick = (lambda lg, i: lg.argmax(-1)) if force_tokens is None else (lambda lg, i: torch.tensor([int(force_tokens[i])]))
+        tok = pick(logits, 0)
         gen = [tok]
-        for _ in range(max_new_tokens - 1):
+        for i in range(1, max_new_tokens if force_tokens is None else len(force_tokens)):
             p = torch.tensor([[self.cache.get_seq_length()]])
             out = self.lm(input_ids=tok[None], past_key_values=self.cache, position_ids=p, use_cache=True)
-            tok = out.logits[:, -1].float().argmax(-1)
+            lg = out.logits[:, -1].float()
+            self.step_logits.append(lg[0].clone())
+            tok = pick(lg, i)
             gen.append(tok)
         n_gen = len(gen)
         self.prev_n_gen = n_gen

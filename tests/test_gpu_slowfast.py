@@ -35,7 +35,7 @@ def test_slowfast_turns_match_oracle(svln_lib, cuda, window_turns, memory_cap, p
     feats = m.vision(frames.to(cuda)).float().cpu()
     out_ids = None
     past = None
-    worst = 0.0
+    exact = total = 0
     for k in range(n_turns):
         t = 4 * k
         if k == 0:
@@ -47,9 +47,15 @@ def test_slowfast_turns_match_oracle(svln_lib, cuda, window_turns, memory_cap, p
                        poses=torch.from_numpy(pose)[None, None], intrinsics=torch.from_numpy(intr)[None, None], env_id=0,
                        time_ids=[[t]], frame_ids=[k], max_new_tokens=n_gen, past_key_values=past)
         past = r.past_key_values
-        seq_o = o.generate(list(ids), feats[k:k + 1], depth, pose, intr, t, n_gen)
-        assert r.sequences.cpu().tolist() == seq_o.tolist(), f"turn {k}"
-        out_ids = seq_o[0].tolist()
+        got = r.sequences.cpu()[0].tolist()
+        # the oracle is teacher-forced with the product's ids, so both follow the same history through a near-tie;
+        # every product token must be a greedy choice under the oracle's logits (identical argmax up to 2e-2 ties)
+        o.generate(list(ids), feats[k:k + 1], depth, pose, intr, t, n_gen, force_tokens=got)
+        ok, n_exact, gap = glue.greedy_consistent(o.step_logits, got)
+        assert ok, f"turn {k}: product tokens {got} are not greedy under the oracle (worst gap {gap:.4f})"
+        exact += n_exact
+        total += len(got)
+        out_ids = got
         sf = m.sf[0]
         # integer state: bit-exact
         assert m.engine.arena.lens[0] == o.cache.get_seq_length(), f"turn {k}"
@@ -57,6 +63,7 @@ def test_slowfast_turns_match_oracle(svln_lib, cuda, window_turns, memory_cap, p
         assert [(u.row_start, u.n_rows) for u in sf.turns] == [(u["row_start"], u["n_rows"]) for u in o.turns]
         assert len(sf.turns) <= window_turns and sf.mem_keys.numel() <= memory_cap
     assert sf.evictions == n_turns - window_turns
+    assert exact >= total - 2, (exact, total)   # at most a couple of genuine near-ties in 36 greedy steps
     # K/V rows of the live cache agree with the oracle's (bf16 vs fp32 + re-rotation rounding)
     L = m.engine.arena.lens[0]
     for layer in range(cfg.llm.num_hidden_layers):
