@@ -122,6 +122,18 @@ int svln_voxel_prune_host(const float* depth_host, const float* pose_host,
                           int32_t* idx_out_host, int32_t* stream_keep_off_out_host,
                           int32_t* n_keep_out_host, void* feat_out_host, svln_stream_t stream);
 
+/* RGB frame preprocessing, replacing the host-side SigLipImageProcessor.preprocess
+ * (llava/model/multimodal_encoder/siglip_encoder.py:34-66, called at streamvln_agent.py:179): Pillow's 8-bit
+ * BICUBIC resample (horizontal then vertical pass, 22-bit fixed-point taps, uint8 rounding per pass) + rescale
+ * 1/255 + normalise (0.5, 0.5), bit-exact.  rgb [n,H,W,3] u8 -> out [n,3,out_h,out_w] f32.  The tap tables
+ * (xmin/xcnt [out_w], xkk [out_w,xksize]; ymin/ycnt [out_h], ykk [out_h,yksize]; i32, device) are Pillow's
+ * precompute_coeffs + normalize_coeffs_8bpc, computed once on the host (streamvln_b200/preprocess.py). */
+size_t svln_preprocess_workspace_bytes(int n, int H, int out_w);
+int svln_preprocess_rgb(const uint8_t* rgb, int n, int H, int W, int out_h, int out_w, const int32_t* xmin,
+                        const int32_t* xcnt, const int32_t* xkk, int xksize, const int32_t* ymin,
+                        const int32_t* ycnt, const int32_t* ykk, int yksize, void* workspace,
+                        size_t workspace_bytes, float* out, svln_stream_t stream);
+
 /* Device-side embed splice, replacing the Python loop of torch.where/.tolist()/torch.cat in
  * prepare_inputs_labels_for_multimodal (stream_video_vln.py:182-238).  row_src[r] >= 0 selects
  * row row_src[r] of `embed_table` (token embedding); row_src[r] < 0 selects row (-row_src[r]-1)

@@ -54,6 +54,13 @@ class VLNEvaluator:
         self.num_history = args.num_history
         self.max_new_tokens = getattr(args, "max_new_tokens", 10000)  # streamvln_agent.py:244
         self.slowfast = model.config.mode == "slowfast"
+        # the image processor runs on the GPU (bit-exact with the PIL path); args.gpu_preprocess=False keeps PIL
+        self.gpu_preprocess = getattr(args, "gpu_preprocess", True)
+        if self.gpu_preprocess:
+            from .preprocess import GpuImageProcessor
+
+            self.gpu_proc = GpuImageProcessor(self.device, self.image_processor.crop_size["height"])
+        self._pin = None
         self._regex = re.compile("|".join(re.escape(a) for a in self.actions2idx))
         self._init_state()
 
@@ -122,8 +129,18 @@ class VLNEvaluator:
         intrinsic = torch.from_numpy(np.asarray(self.intrinsic_matrix if intrinsic is None else intrinsic)).float()
         # Step 1: preprocess the image only on model steps; other steps repeat the last one (:177-184)
         if run_model:
+            self.h2d_bytes = 0
             if preprocessed is not None:
                 image = preprocessed
+            elif self.gpu_preprocess:
+                # uint8 frame -> pinned staging -> device; PIL-exact bicubic + normalise run as CUDA kernels
+                u8 = torch.from_numpy(np.ascontiguousarray(np.asarray(rgb)[..., :3]))
+                if self._pin is None or self._pin.shape != u8.shape:
+                    self._pin = torch.empty(u8.shape, dtype=torch.uint8).pin_memory()
+                self._pin.copy_(u8)
+                image = self.gpu_proc(self._pin.to(self.device, non_blocking=True)[None])[0]
+                self.h2d_bytes = u8.numel()
+                self.model.engine.launches += 2
             else:
                 from PIL import Image
 
@@ -177,10 +194,10 @@ class VLNEvaluator:
         # frames repeated on non-model steps are the same image: key the feature cache by the model-step frame
         frame_ids = [self._source_frame(i) for i in sel]
         # Step 4: generate (:242-246).  One pinned-memory H2D per turn for the frames.
-        self.h2d_bytes = 0
         if not images.is_cuda:
-            self.h2d_bytes = images.numel() * images.element_size() + input_ids.numel() * 8
+            self.h2d_bytes = images.numel() * images.element_size()
             images = images.pin_memory().to(self.device, non_blocking=True)
+        self.h2d_bytes = getattr(self, "h2d_bytes", 0) + input_ids.numel() * 8
         return dict(inputs=input_ids, images=images, depths=depths, poses=poses, intrinsics=intrinsics, env_id=idx,
                     time_ids=[list(self.time_ids)], task_ids=[0], frame_ids=frame_ids, do_sample=False, num_beams=1,
                     max_new_tokens=self.max_new_tokens, use_cache=True, return_dict_in_generate=True,

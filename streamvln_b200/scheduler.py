@@ -91,7 +91,7 @@ class BatchedEvaluator:
                  geom: Optional[Dict[int, dict]] = None, preprocessed: Optional[Dict[int, torch.Tensor]] = None):
         """One env step for every live stream.  Returns {stream: action list} on a model step, else {}."""
         reqs, who = [], []
-        if run_model and frames and preprocessed is None and len(live) > 1:
+        if run_model and frames and preprocessed is None and len(live) > 1 and not self.agents[0].gpu_preprocess:
             # host uint8 frames: run the PIL image processor of all streams on a thread pool (PIL drops the GIL)
             from concurrent.futures import ThreadPoolExecutor
             from PIL import Image

@@ -178,3 +178,20 @@ def test_agent_actions_match_oracle_agent(tiny, cuda):
         oa.step_id += 1
     assert got == want
     assert sum(a is not None for a in got) == 10 and exact >= 38
+
+
+def test_gpu_image_processor_matches_pil(svln_lib, cuda):
+    """svln_preprocess_rgb == the reference's PIL image processor, bit for bit."""
+    from PIL import Image
+    from streamvln_b200.preprocess import GpuImageProcessor
+    from streamvln_b200.vision import SigLipImageProcessor
+
+    rng = np.random.default_rng(0)
+    proc, gpu = SigLipImageProcessor(), GpuImageProcessor(cuda)
+    for h, w in ((480, 640), (720, 1280), (384, 384), (97, 131)):
+        frames = rng.integers(0, 256, size=(2, h, w, 3), dtype=np.uint8)
+        frames[0, : h // 2] = np.linspace(0, 255, w)[None, :, None].astype(np.uint8)
+        got = gpu(torch.from_numpy(frames).to(cuda)).cpu()
+        for i in range(2):
+            want = proc.preprocess(images=Image.fromarray(frames[i]), return_tensors="pt")["pixel_values"][0]
+            assert torch.equal(got[i], want), (h, w, i)
