@@ -37,13 +37,13 @@ constexpr int PF_MAX_SEQ = 64;
 constexpr int SM_Q = 0;
 constexpr int SM_K = SM_Q + PF_TILE;           // 2 stages
 constexpr int SM_V = SM_K + 2 * PF_TILE;       // 2 stages
-constexpr int SM_P = SM_V + 2 * PF_TILE;
-constexpr int SM_BAR = SM_P + PF_TILE;         // barriers + tmem pointer
-constexpr int SM_XCH = SM_BAR + 256;           // float [2 tiles][2 halves][128 rows] row-max exchange
-constexpr int PF_SMEM = SM_XCH + 3 * 2 * 128 * 4 + 1024;   // (+ one [2][128] block for the row-sum exchange) + alignment slack
+constexpr int SM_P = SM_V + 2 * PF_TILE;       // 2 buffers: softmax(j+1) writes P while PV(j) still reads P(j)
+constexpr int SM_BAR = SM_P + 2 * PF_TILE;     // barriers + tmem pointer
+constexpr int SM_XCH = SM_BAR + 256;           // float [2 tiles][2 halves][128 rows] row-max exchange (reused for the row sums)
+constexpr int PF_SMEM = SM_XCH + 2 * 2 * 128 * 4;  // 231 680 B of the 232 448 B a CTA may own: the base must be 1024-aligned
 
 enum { BAR_K_FULL = 0, BAR_K_EMPTY = 2, BAR_V_FULL = 4, BAR_V_EMPTY = 6, BAR_S_FULL = 8, BAR_S_EMPTY = 10,
-       BAR_P_FULL = 12, BAR_PV_DONE = 13, BAR_COUNT = 14 };
+       BAR_P_FULL = 12, BAR_PV_DONE = 14, BAR_COUNT = 16 };
 
 struct PrefillParams {
     const __nv_bfloat16* q;   // [n_tok, Hq, 128]
@@ -119,6 +119,18 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+// explicit shared-space accesses (the compiler only sees a generic pointer after the carve-up)
+__device__ __forceinline__ void sts128(uint32_t addr, const int4& v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void sts32f(uint32_t addr, float v) {
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ float lds32f(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+    return v;
+}
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -154,9 +166,9 @@ __device__ __forceinline__ uint32_t kmajor_off(int r, int c) {
 
 __global__ void __launch_bounds__(PF_THREADS, 1)
 attn_prefill_kernel(const __grid_constant__ CUtensorMap kv_map, const __grid_constant__ PrefillParams p) {
-    extern __shared__ unsigned char smem_raw[];
-    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    extern __shared__ __align__(1024) unsigned char smem[];
     const uint32_t sbase = s2u(smem);
+    if ((sbase & 1023u) != 0) __trap();  // SWIZZLE_128B tiles need a 1024-byte aligned base (no static smem in this kernel)
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + SM_BAR + BAR_COUNT * 8);
     const uint32_t bar0 = sbase + SM_BAR;
     auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
@@ -166,9 +178,11 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap kv_map, const __grid_con
     const int g = p.n_q_head / p.n_kv_head;
 
     // locate (sequence, M tile)
+    // heaviest tiles first: within a sequence later M tiles see more keys (causal), so walk the grid backwards
+    const int gtile = (int)gridDim.x - 1 - (int)blockIdx.x;
     int b = 0;
-    while (b + 1 < p.n_seq && (int)blockIdx.x >= p.tile_start[b + 1]) ++b;
-    const int mtile = blockIdx.x - p.tile_start[b];
+    while (b + 1 < p.n_seq && gtile >= p.tile_start[b + 1]) ++b;
+    const int mtile = gtile - p.tile_start[b];
     const bool dev = p.d_env != nullptr;
     const int nq = dev ? p.d_n_q[b] : p.n_q[b];
     const int len = dev ? p.d_kv_len[b] : p.kv_len[b];
@@ -189,9 +203,11 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap kv_map, const __grid_con
         mbar_init(BAR(BAR_V_FULL), 1); mbar_init(BAR(BAR_V_FULL + 1), 1);
         mbar_init(BAR(BAR_V_EMPTY), 1); mbar_init(BAR(BAR_V_EMPTY + 1), 1);
         mbar_init(BAR(BAR_S_FULL), 1); mbar_init(BAR(BAR_S_FULL + 1), 1);
-        mbar_init(BAR(BAR_S_EMPTY), PF_SOFTMAX_WARPS * 32); mbar_init(BAR(BAR_S_EMPTY + 1), PF_SOFTMAX_WARPS * 32);
-        mbar_init(BAR(BAR_P_FULL), PF_SOFTMAX_WARPS * 32);
-        mbar_init(BAR(BAR_PV_DONE), 1);
+        // one arrival per softmax warp (elected lane after __syncwarp), not one per thread: 512 shared-memory
+        // atomics per tile would serialise on the barrier word
+        mbar_init(BAR(BAR_S_EMPTY), PF_SOFTMAX_WARPS); mbar_init(BAR(BAR_S_EMPTY + 1), PF_SOFTMAX_WARPS);
+        mbar_init(BAR(BAR_P_FULL), PF_SOFTMAX_WARPS); mbar_init(BAR(BAR_P_FULL + 1), PF_SOFTMAX_WARPS);
+        mbar_init(BAR(BAR_PV_DONE), 1); mbar_init(BAR(BAR_PV_DONE + 1), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {  // TMEM allocation: 512 columns, by one full warp (which also frees it)
@@ -214,7 +230,7 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap kv_map, const __grid_con
             for (int c = 0; c < 8; ++c) v[c] = make_int4(0, 0, 0, 0);
         }
 #pragma unroll
-        for (int c = 0; c < 8; ++c) *reinterpret_cast<int4*>(smem + SM_Q + kmajor_off(r, half * 8 + c)) = v[c];
+        for (int c = 0; c < 8; ++c) sts128(sbase + SM_Q + kmajor_off(r, half * 8 + c), v[c]);
     }
     fence_async_smem();  // make the generic-proxy smem writes visible to the async proxy (MMA)
     tc_fence_before();
@@ -271,7 +287,7 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap kv_map, const __grid_con
                     tc_commit(BAR(BAR_S_FULL + s));
                 }
                 const int s = j & 1, u = j >> 1;
-                mbar_wait(BAR(BAR_P_FULL), j & 1);
+                mbar_wait(BAR(BAR_P_FULL + s), u & 1);
                 mbar_wait(BAR(BAR_V_FULL + s), u & 1);
                 tc_fence_after();
                 const uint32_t vb = sbase + SM_V + s * PF_TILE;
@@ -280,11 +296,11 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap kv_map, const __grid_con
                     // A = P: K-major (keys contiguous), 4 steps per 64-key panel
                     const uint32_t aoff = (ks >> 2) * PF_PANEL + (ks & 3) * 32;
                     // B = V: MN-major; 16 keys = two 8-row swizzle atoms = 2048 B; dims panels 16 KB apart
-                    tc_mma(TM_O, umma_desc(sbase + SM_P + aoff, 16, 1024), umma_desc(vb + ks * 2048, PF_PANEL, 1024),
+                    tc_mma(TM_O, umma_desc(sbase + SM_P + s * PF_TILE + aoff, 16, 1024), umma_desc(vb + ks * 2048, PF_PANEL, 1024),
                            IDESC_PV, (j > 0 || ks > 0));
                 }
                 tc_commit(BAR(BAR_V_EMPTY + s));
-                tc_commit(BAR(BAR_PV_DONE));
+                tc_commit(BAR(BAR_PV_DONE + s));
             }
         }
     } else {
@@ -297,7 +313,7 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap kv_map, const __grid_con
         const int hg = row_valid ? R - tq * g : 0;
         const int lim = row_valid ? len - nq + tq + 1 : 0;   // keys < lim are visible
         const uint32_t lane_addr = ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(half * 64);
-        float* xch = reinterpret_cast<float*>(smem + SM_XCH);  // [tile parity][half][row]
+        const uint32_t xch = sbase + SM_XCH;                   // float [tile parity][half][row], shared-space address
         const int pair_bar = 1 + (warp & 3);                   // named barrier shared by warps w and w+4
         float m_used = -INFINITY;   // running reference max in scaled (log2) units; identical in both halves
         float l_sum = 0.f;          // this thread's half of the row sum
@@ -310,7 +326,8 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap kv_map, const __grid_con
             for (int c = 0; c < 2; ++c) tmem_ld32(TM_S0 + s * 128 + lane_addr + c * 32, sv[c]);
             tmem_wait_ld();
             tc_fence_before();
-            mbar_arrive(BAR(BAR_S_EMPTY + s));
+            __syncwarp();
+            if (lane == 0) mbar_arrive(BAR(BAR_S_EMPTY + s));
             // mask + row max on the raw scores (scale > 0 commutes with max)
             const int key0 = j * PF_BN + half * 64;
             float mx = -INFINITY;
@@ -328,9 +345,9 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap kv_map, const __grid_con
 #pragma unroll
                     for (int e = 0; e < 32; ++e) mx = fmaxf(mx, __uint_as_float(sv[c][e]));
             }
-            xch[(s * 2 + half) * 128 + r] = mx;
+            sts32f(xch + ((s * 2 + half) * 128 + r) * 4, mx);
             asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
-            mx = fmaxf(mx, xch[(s * 2 + (half ^ 1)) * 128 + r]) * p.scale_log2;
+            mx = fmaxf(mx, lds32f(xch + ((s * 2 + (half ^ 1)) * 128 + r) * 4)) * p.scale_log2;
             // lazy rescale: only move the reference max when it grew by more than 8 (factor 256)
             float alpha = 1.f;
             bool rescale = false;
@@ -340,11 +357,13 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap kv_map, const __grid_con
                 rescale = j > 0;
             }
             const float neg_m = m_used == -INFINITY ? 0.f : -m_used;
-            // P buffer and O are free once PV(j-1) has completed
-            if (j > 0) mbar_wait(BAR(BAR_PV_DONE), (j - 1) & 1);
-            tc_fence_after();
+            // P buffer s is free once PV(j-2) has completed (long ago in steady state: PV(j-1) is what may still run)
+            if (j > 1) mbar_wait(BAR(BAR_PV_DONE + s), (u - 1) & 1);
             l_sum *= alpha;
             if (__any_sync(0xffffffffu, rescale)) {
+                // rare (lazy rescale): O must be quiescent, i.e. PV(j-1) done; PV(j) cannot start before our P(j)
+                mbar_wait(BAR(BAR_PV_DONE + (s ^ 1)), ((j - 1) >> 1) & 1);
+                tc_fence_after();
 #pragma unroll
                 for (int c = 0; c < 2; ++c) {
                     uint32_t ov[32];
@@ -370,19 +389,21 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap kv_map, const __grid_con
                         psum += p0 + p1;
                         w[e] = pack2_bf16(p0, p1);
                     }
-                    *reinterpret_cast<int4*>(smem + SM_P + kmajor_off(r, half * 8 + c * 4 + q)) = make_int4(w[0], w[1], w[2], w[3]);
+                    sts128(sbase + SM_P + s * PF_TILE + kmajor_off(r, half * 8 + c * 4 + q), make_int4(w[0], w[1], w[2], w[3]));
                 }
             }
             l_sum += psum;
             fence_async_smem();
             tc_fence_before();
-            mbar_arrive(BAR(BAR_P_FULL));
+            __syncwarp();
+            if (lane == 0) mbar_arrive(BAR(BAR_P_FULL + s));
         }
         // epilogue: O / l -> bf16 -> global (this thread: 64 dims of its row)
-        xch[(4 + half) * 128 + r] = l_sum;   // separate block: the partner may still be reading the last row max
+        asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");   // partner has read the last row max: reuse the block
+        sts32f(xch + (half * 128 + r) * 4, l_sum);
         asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
-        const float l_tot = l_sum + xch[(4 + (half ^ 1)) * 128 + r];
-        mbar_wait(BAR(BAR_PV_DONE), (n_tiles - 1) & 1);
+        const float l_tot = l_sum + lds32f(xch + ((half ^ 1) * 128 + r) * 4);
+        mbar_wait(BAR(BAR_PV_DONE + ((n_tiles - 1) & 1)), ((n_tiles - 1) >> 1) & 1);
         tc_fence_after();
         const float inv_l = l_tot > 0.f ? 1.0f / l_tot : 0.f;
         __nv_bfloat16* orow = p.out + ((int64_t)(qs + tq) * p.n_q_head + kvh * g + hg) * PF_HD + half * 64;
