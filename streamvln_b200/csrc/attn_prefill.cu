@@ -18,6 +18,7 @@
 //               64-column SWIZZLE_128B panels each) into 2-stage rings.
 // TMEM: S0 cols [0,128), S1 [128,256), O [256,384) of a 512-column allocation.
 #include <cuda.h>
+#include <stdlib.h>
 #include <cudaTypedefs.h>
 
 #include "svln_common.cuh"
@@ -50,6 +51,7 @@ struct PrefillParams {
     __nv_bfloat16* out;       // [n_tok, Hq*128]
     int n_q_head, n_kv_head, n_layer, layer, max_len;
     int n_seq;
+    int debug;  // SVLN_PF_DEBUG bit flags for bottleneck experiments (0 in production): 1 = no MUFU, 2 = no P store
     float scale_log2;
     // sequence descriptors: device arrays when d_env != nullptr (CUDA-graph replayable: only the grid
     // shape, i.e. n_q, is baked into the launch), else the by-value copies below
@@ -384,12 +386,14 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap kv_map, const __grid_con
                     uint32_t w[4];
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
-                        const float p0 = ex2_approx(fmaf(__uint_as_float(sv[c][q * 8 + 2 * e]), p.scale_log2, neg_m));
-                        const float p1 = ex2_approx(fmaf(__uint_as_float(sv[c][q * 8 + 2 * e + 1]), p.scale_log2, neg_m));
+                        float p0 = fmaf(__uint_as_float(sv[c][q * 8 + 2 * e]), p.scale_log2, neg_m);
+                        float p1 = fmaf(__uint_as_float(sv[c][q * 8 + 2 * e + 1]), p.scale_log2, neg_m);
+                        if (!(p.debug & 1)) { p0 = ex2_approx(p0); p1 = ex2_approx(p1); }
                         psum += p0 + p1;
                         w[e] = pack2_bf16(p0, p1);
                     }
-                    sts128(sbase + SM_P + s * PF_TILE + kmajor_off(r, half * 8 + c * 4 + q), make_int4(w[0], w[1], w[2], w[3]));
+                    if (!(p.debug & 2))
+                        sts128(sbase + SM_P + s * PF_TILE + kmajor_off(r, half * 8 + c * 4 + q), make_int4(w[0], w[1], w[2], w[3]));
                 }
             }
             l_sum += psum;
@@ -501,6 +505,8 @@ static int prefill_launch(const svln_kv_arena* arena, int layer, const void* q, 
         p.n_q_head = n_q_head; p.n_kv_head = arena->n_kv_head; p.n_layer = arena->n_layer; p.layer = layer;
         p.max_len = arena->max_len;
         p.scale_log2 = scale * 1.4426950408889634f;
+        static const int dbg = getenv("SVLN_PF_DEBUG") ? atoi(getenv("SVLN_PF_DEBUG")) : 0;
+        p.debug = dbg;
         const int ns = n_seq - s0 < PF_MAX_SEQ ? n_seq - s0 : PF_MAX_SEQ;
         p.n_seq = ns;
         p.d_env = dev ? env_d + s0 : nullptr;
