@@ -17,11 +17,9 @@
 //   warp 9    : one elected thread issues TMA loads of K and V tiles (128 keys x 128 dims, two
 //               64-column SWIZZLE_128B panels each) into 2-stage rings.
 // TMEM: S0 cols [0,128), S1 [128,256), O [256,384) of a 512-column allocation.
-#include <cuda.h>
 #include <stdlib.h>
-#include <cudaTypedefs.h>
 
-#include "svln_common.cuh"
+#include "tcgen05_helpers.cuh"
 
 namespace svln {
 
@@ -59,107 +57,6 @@ struct PrefillParams {
     int32_t env[PF_MAX_SEQ], q_start[PF_MAX_SEQ], n_q[PF_MAX_SEQ], kv_len[PF_MAX_SEQ];
     int32_t tile_start[PF_MAX_SEQ + 1];  // prefix sum of M tiles per sequence (from the host-known n_q)
 };
-
-// ---------------------------------------------------------------------------- PTX wrappers
-__device__ __forceinline__ uint32_t s2u(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra WAIT_DONE;\n\t"
-        "bra WAIT_LOOP;\n\t"
-        "WAIT_DONE:\n\t}" ::"r"(bar), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accum) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accum) : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr) : "memory");
-}
-__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-        "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
-        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
-          "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
-          "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
-          "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
-        : "memory");
-}
-__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-
-// explicit shared-space accesses (the compiler only sees a generic pointer after the carve-up)
-__device__ __forceinline__ void sts128(uint32_t addr, const int4& v) {
-    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-}
-__device__ __forceinline__ void sts32f(uint32_t addr, float v) {
-    asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
-}
-__device__ __forceinline__ float lds32f(uint32_t addr) {
-    float v;
-    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
-    return v;
-}
-__device__ __forceinline__ float ex2_approx(float x) {
-    float y;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-// two fp32 -> packed bf16x2 (lo in bits [0,16)), round-to-nearest-even, one instruction
-__device__ __forceinline__ uint32_t pack2_bf16(float lo, float hi) {
-    uint32_t r;
-    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
-    return r;
-}
-
-// Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): SWIZZLE_128B, version 1.
-//   bits [0,14) start>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version=1 | [61,64) layout=2
-__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
-    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
-    return d;
-}
-// Instruction descriptor (cute::UMMA::InstrDescriptor), kind::f16, bf16 x bf16 -> f32, M=128, N=128
-__host__ __device__ constexpr uint32_t umma_idesc(int b_mn_major) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)b_mn_major << 16) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
-}
 
 // byte offset of 16-byte chunk c (0..15) of row r inside a K-major [128][128] SW128 tile (two panels)
 __device__ __forceinline__ uint32_t kmajor_off(int r, int c) {
@@ -438,14 +335,15 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap kv_map, const __grid_con
 
 // ------------------------------------------------------------------------------ host side
 struct MapCacheEntry {
-    void* base; int n_env, n_layer, n_kv_head, max_len; CUtensorMap map; bool valid;
+    void* base; int n_env, n_layer, n_kv_head, max_len, box_rows; CUtensorMap map; bool valid;
 };
 static MapCacheEntry g_map_cache[8];
 
-static int get_kv_map(const svln_kv_arena* a, CUtensorMap* out) {
+// 3-D tensor map (128 dims, max_len rows, planes) over the whole arena, box = 64 dims x box_rows keys, SWIZZLE_128B
+int get_kv_map(const svln_kv_arena* a, int box_rows, CUtensorMap* out) {
     for (auto& e : g_map_cache)
         if (e.valid && e.base == a->base && e.n_env == a->n_env && e.n_layer == a->n_layer &&
-            e.n_kv_head == a->n_kv_head && e.max_len == a->max_len) {
+            e.n_kv_head == a->n_kv_head && e.max_len == a->max_len && e.box_rows == box_rows) {
             *out = e.map;
             return SVLN_OK;
         }
@@ -460,7 +358,7 @@ static int get_kv_map(const svln_kv_arena* a, CUtensorMap* out) {
     const cuuint64_t planes = (cuuint64_t)a->n_env * a->n_layer * 2 * a->n_kv_head;
     cuuint64_t gdim[3] = {(cuuint64_t)PF_HD, (cuuint64_t)a->max_len, planes};
     cuuint64_t gstride[2] = {(cuuint64_t)PF_HD * 2, (cuuint64_t)a->max_len * PF_HD * 2};
-    cuuint32_t box[3] = {64, (cuuint32_t)PF_BN, 1};
+    cuuint32_t box[3] = {64, (cuuint32_t)box_rows, 1};
     cuuint32_t estride[3] = {1, 1, 1};
     CUtensorMap m;
     CUresult r = encode(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, a->base, gdim, gstride, box, estride,
@@ -469,7 +367,7 @@ static int get_kv_map(const svln_kv_arena* a, CUtensorMap* out) {
     SVLN_REQUIRE(r == CUDA_SUCCESS, SVLN_ERR_CUDA, "cuTensorMapEncodeTiled failed with %d", (int)r);
     static int next = 0;
     MapCacheEntry& e = g_map_cache[next++ % 8];
-    e = {a->base, a->n_env, a->n_layer, a->n_kv_head, a->max_len, m, true};
+    e = {a->base, a->n_env, a->n_layer, a->n_kv_head, a->max_len, box_rows, m, true};
     *out = m;
     return SVLN_OK;
 }
@@ -489,8 +387,12 @@ static int prefill_launch(const svln_kv_arena* arena, int layer, const void* q, 
     const bool dev = env_d != nullptr;
     SVLN_REQUIRE(dev ? (q_start_d && n_q_d && kv_len_d) : (env_h && q_start_h && kv_len_h), SVLN_ERR_INVALID,
                  "%s: null descriptor array", who);
+    static const int version = getenv("SVLN_PF_V") ? atoi(getenv("SVLN_PF_V")) : 4;
+    if (version >= 4)  // 256 rows per CTA (two Q tiles share every K/V tile): half the L2->SM bytes per FLOP
+        return prefill2_launch(arena, layer, q, n_q_head, env_h, q_start_h, n_q_h, kv_len_h, env_d, q_start_d, n_q_d, kv_len_d,
+                               n_seq, scale, out, stream, who);
     CUtensorMap map;
-    int rc = get_kv_map(arena, &map);
+    int rc = get_kv_map(arena, PF_BN, &map);
     if (rc) return rc;
     static bool attr_set = false;
     if (!attr_set) {
