@@ -388,7 +388,10 @@ static int prefill_launch(const svln_kv_arena* arena, int layer, const void* q, 
     SVLN_REQUIRE(dev ? (q_start_d && n_q_d && kv_len_d) : (env_h && q_start_h && kv_len_h), SVLN_ERR_INVALID,
                  "%s: null descriptor array", who);
     static const int version = getenv("SVLN_PF_V") ? atoi(getenv("SVLN_PF_V")) : 4;
-    if (version >= 4)  // 256 rows per CTA (two Q tiles share every K/V tile): half the L2->SM bytes per FLOP
+    if (version >= 5)  // Q and P in tensor memory (TS-form MMAs): shared memory only carries K and V
+        return prefill3_launch(arena, layer, q, n_q_head, env_h, q_start_h, n_q_h, kv_len_h, env_d, q_start_d, n_q_d, kv_len_d,
+                               n_seq, scale, out, stream, who);
+    if (version == 4)  // 256 rows per CTA (two Q tiles share every K/V tile): half the L2->SM bytes per FLOP
         return prefill2_launch(arena, layer, q, n_q_head, env_h, q_start_h, n_q_h, kv_len_h, env_d, q_start_d, n_q_d, kv_len_d,
                                n_seq, scale, out, stream, who);
     CUtensorMap map;

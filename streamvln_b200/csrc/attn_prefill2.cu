@@ -49,7 +49,15 @@ struct Prefill2Params {
     const int32_t *d_env, *d_q_start, *d_n_q, *d_kv_len;  // device descriptors (graph-replayable) or nullptr
     int32_t env[P2_MAX_SEQ], q_start[P2_MAX_SEQ], n_q[P2_MAX_SEQ], kv_len[P2_MAX_SEQ];
     int32_t tile_start[P2_MAX_SEQ + 1];                    // prefix sum of 256-row CTA tiles per sequence
+    long long* trace;                                      // SVLN_PF_TRACE: per-phase clock64 stamps of CTA (0,0), else nullptr
 };
+
+// trace layout: [role 0..3][tile 0..31][slot 0..7]; roles: 0 softmax warp 0, 1 softmax warp 4, 2 MMA thread, 3 TMA thread
+#define P2_TRACE(role, tile, slot)                                                                     \
+    do {                                                                                               \
+        if (p.trace && blockIdx.x == gridDim.x / 2 && blockIdx.y == 0 && (tile) < 32 && ((role) < 2 || lane == 0)) \
+            p.trace[((role) * 32 + (tile)) * 8 + (slot)] = clock64();                                  \
+    } while (0)
 
 __global__ void __launch_bounds__(P2_THREADS, 1)
 attn_prefill2_kernel(const __grid_constant__ CUtensorMap kv_map, const __grid_constant__ Prefill2Params p) {
@@ -129,62 +137,79 @@ attn_prefill2_kernel(const __grid_constant__ CUtensorMap kv_map, const __grid_co
 
     if (warp == P2_SOFTMAX_WARPS + 1) {
         // ------------------------------------------------------------ TMA producer
-        if (lane == 0) {
-            asm volatile("prefetch.tensormap [%0];" ::"l"(&kv_map) : "memory");
-            for (int j = 0; j < n_tiles; ++j) {
-                const int st = j % P2_STAGES, u = j / P2_STAGES;
-                const int key0 = j * P2_BN;
-                mbar_wait(BAR(B2_K_EMPTY + st), (u & 1) ^ 1);
+        // the whole warp runs the (uniform) control flow; one elected lane issues
+        if (elect_one()) asm volatile("prefetch.tensormap [%0];" ::"l"(&kv_map) : "memory");
+        for (int j = 0; j < n_tiles; ++j) {
+            const int st = j % P2_STAGES, u = j / P2_STAGES;
+            const int key0 = j * P2_BN;
+            mbar_wait(BAR(B2_K_EMPTY + st), (u & 1) ^ 1);
+            if (elect_one()) {
                 mbar_expect_tx(BAR(B2_K_FULL + st), P2_KVTILE);
                 tma_load_3d(sbase + S2_K + st * P2_KVTILE, &kv_map, BAR(B2_K_FULL + st), 0, key0, plane_k);
                 tma_load_3d(sbase + S2_K + st * P2_KVTILE + P2_KVPANEL, &kv_map, BAR(B2_K_FULL + st), 64, key0, plane_k);
-                mbar_wait(BAR(B2_V_EMPTY + st), (u & 1) ^ 1);
+            }
+            mbar_wait(BAR(B2_V_EMPTY + st), (u & 1) ^ 1);
+            if (elect_one()) {
                 mbar_expect_tx(BAR(B2_V_FULL + st), P2_KVTILE);
                 tma_load_3d(sbase + S2_V + st * P2_KVTILE, &kv_map, BAR(B2_V_FULL + st), 0, key0, plane_v);
                 tma_load_3d(sbase + S2_V + st * P2_KVTILE + P2_KVPANEL, &kv_map, BAR(B2_V_FULL + st), 64, key0, plane_v);
             }
+            __syncwarp();
         }
     } else if (warp == P2_SOFTMAX_WARPS) {
         // ------------------------------------------------------------ MMA issuer
-        if (lane == 0) {
-            constexpr uint32_t IDESC_QK = umma_idesc(0, 64);    // S tile: N = 64 keys
-            constexpr uint32_t IDESC_PV = umma_idesc(1, 128);   // O tile: N = 128 dims, V MN-major
-            auto issue_qk = [&](int j) {
-                const int st = j % P2_STAGES, bf = j & 1, ub = j >> 1;
-                mbar_wait(BAR(B2_K_FULL + st), (j / P2_STAGES) & 1);
-                const uint32_t kb = sbase + S2_K + st * P2_KVTILE;
+        // The whole warp executes this warp-uniform control flow and only the tcgen05 instructions sit under an
+        // elected-lane predicate: descriptors then live in uniform registers.  (Issuing from `if (lane == 0)` made
+        // ptxas wrap every UTCHMMA in an R2UR + waterfall loop: ~80 cycles per MMA, the measured bottleneck.)
+        constexpr uint32_t IDESC_QK = umma_idesc(0, 64);    // S tile: N = 64 keys
+        constexpr uint32_t IDESC_PV = umma_idesc(1, 128);   // O tile: N = 128 dims, V MN-major
+        auto issue_qk = [&](int j) {
+            const int st = j % P2_STAGES, bf = j & 1, ub = j >> 1;
+            P2_TRACE(2, j, 0);
+            mbar_wait(BAR(B2_K_FULL + st), (j / P2_STAGES) & 1);
+            P2_TRACE(2, j, 1);
+            const uint32_t kb = sbase + S2_K + st * P2_KVTILE;
 #pragma unroll
-                for (int t = 0; t < P2_NQT; ++t) {
-                    mbar_wait(BAR(B2_S_EMPTY + t * 2 + bf), (ub & 1) ^ 1);
-                    tc_fence_after();
-                    const uint32_t qb = sbase + S2_Q + t * P2_QTILE;
+            for (int t = 0; t < P2_NQT; ++t) {
+                mbar_wait(BAR(B2_S_EMPTY + t * 2 + bf), (ub & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t qb = sbase + S2_Q + t * P2_QTILE;
+                if (elect_one()) {
 #pragma unroll
                     for (int ks = 0; ks < 8; ++ks)
                         tc_mma(TM_S(t, bf), umma_desc(qb + (ks >> 2) * P2_QPANEL + (ks & 3) * 32, 16, 1024),
                                umma_desc(kb + (ks >> 2) * P2_KVPANEL + (ks & 3) * 32, 16, 1024), IDESC_QK, ks > 0);
                     tc_commit(BAR(B2_S_FULL + t * 2 + bf));
+                    if (t == P2_NQT - 1) tc_commit(BAR(B2_K_EMPTY + st));
                 }
-                tc_commit(BAR(B2_K_EMPTY + st));
-            };
-            issue_qk(0);
-            for (int j = 0; j < n_tiles; ++j) {
-                if (j + 1 < n_tiles) issue_qk(j + 1);
-                const int st = j % P2_STAGES, bf = j & 1, ub = j >> 1;
-                mbar_wait(BAR(B2_V_FULL + st), (j / P2_STAGES) & 1);
-                const uint32_t vb = sbase + S2_V + st * P2_KVTILE;
+                __syncwarp();
+            }
+            P2_TRACE(2, j, 2);
+        };
+        issue_qk(0);
+        for (int j = 0; j < n_tiles; ++j) {
+            if (j + 1 < n_tiles) issue_qk(j + 1);
+            const int st = j % P2_STAGES, bf = j & 1, ub = j >> 1;
+            mbar_wait(BAR(B2_V_FULL + st), (j / P2_STAGES) & 1);
+            P2_TRACE(2, j, 3);
+            const uint32_t vb = sbase + S2_V + st * P2_KVTILE;
 #pragma unroll
-                for (int t = 0; t < P2_NQT; ++t) {
-                    mbar_wait(BAR(B2_P_FULL + t * 2 + bf), ub & 1);
-                    tc_fence_after();
-                    const uint32_t pb = sbase + S2_P + (t * 2 + bf) * P2_PTILE;
+            for (int t = 0; t < P2_NQT; ++t) {
+                mbar_wait(BAR(B2_P_FULL + t * 2 + bf), ub & 1);
+                P2_TRACE(2, j, 4 + t);
+                tc_fence_after();
+                const uint32_t pb = sbase + S2_P + (t * 2 + bf) * P2_PTILE;
+                if (elect_one()) {
 #pragma unroll
                     for (int ks = 0; ks < 4; ++ks)   // 16 keys per step: P k-advance 32 B; V k-advance 16 rows x 128 B
                         tc_mma(TM_O(t), umma_desc(pb + ks * 32, 16, 1024), umma_desc(vb + ks * 2048, P2_KVPANEL, 1024), IDESC_PV,
                                (j > 0 || ks > 0));
                     tc_commit(BAR(B2_PV_DONE + t * 2 + bf));
+                    if (t == P2_NQT - 1) tc_commit(BAR(B2_V_EMPTY + st));
                 }
-                tc_commit(BAR(B2_V_EMPTY + st));
+                __syncwarp();
             }
+            P2_TRACE(2, j, 6);
         }
     } else {
         // ------------------------------------------------------------ softmax warps
@@ -199,7 +224,10 @@ attn_prefill2_kernel(const __grid_constant__ CUtensorMap kv_map, const __grid_co
         float m_used = -INFINITY, l_sum = 0.f;
         for (int j = 0; j < n_tiles; ++j) {
             const int bf = j & 1, ub = j >> 1;
+            const int trole = (lane == 0 && (warp & 3) == 0) ? t : 99;
+            if (trole < 2) P2_TRACE(trole, j, 0);
             mbar_wait(BAR(B2_S_FULL + t * 2 + bf), ub & 1);
+            if (trole < 2) P2_TRACE(trole, j, 1);
             tc_fence_after();
             uint32_t sv[2][32];
             tmem_ld32(TM_S(t, bf) + lane_addr, sv[0]);
@@ -208,6 +236,7 @@ attn_prefill2_kernel(const __grid_constant__ CUtensorMap kv_map, const __grid_co
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(BAR(B2_S_EMPTY + t * 2 + bf));
+            if (trole < 2) P2_TRACE(trole, j, 2);
             const int key0 = j * P2_BN;
             float mx = -INFINITY;
             if (key0 + P2_BN > lim) {
@@ -233,7 +262,9 @@ attn_prefill2_kernel(const __grid_constant__ CUtensorMap kv_map, const __grid_co
                 rescale = j > 0;
             }
             const float neg_m = m_used == -INFINITY ? 0.f : -m_used;
+            if (trole < 2) P2_TRACE(trole, j, 3);
             if (j > 1) mbar_wait(BAR(B2_PV_DONE + t * 2 + bf), (ub - 1) & 1);          // P[t][bf] free: PV_t(j-2) done
+            if (trole < 2) P2_TRACE(trole, j, 4);
             l_sum *= alpha;
             if (__any_sync(0xffffffffu, rescale)) {
                 mbar_wait(BAR(B2_PV_DONE + t * 2 + (bf ^ 1)), ((j - 1) >> 1) & 1);      // O_t quiescent: PV_t(j-1) done
@@ -267,10 +298,12 @@ attn_prefill2_kernel(const __grid_constant__ CUtensorMap kv_map, const __grid_co
                     sts128(pb + (((c * 4 + q) ^ (r & 7)) << 4), make_int4(w[0], w[1], w[2], w[3]));
                 }
             l_sum += psum;
+            if (trole < 2) P2_TRACE(trole, j, 5);
             fence_async_smem();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(BAR(B2_P_FULL + t * 2 + bf));
+            if (trole < 2) P2_TRACE(trole, j, 6);
         }
         // epilogue
         mbar_wait(BAR(B2_PV_DONE + t * 2 + ((n_tiles - 1) & 1)), ((n_tiles - 1) >> 1) & 1);
@@ -323,6 +356,7 @@ int prefill2_launch(const svln_kv_arena* arena, int layer, const void* q, int n_
         p.n_q_head = n_q_head; p.n_kv_head = arena->n_kv_head; p.n_layer = arena->n_layer; p.layer = layer;
         p.max_len = arena->max_len;
         p.scale_log2 = scale * 1.4426950408889634f;
+        p.trace = getenv("SVLN_PF_TRACE") ? (long long*)strtoull(getenv("SVLN_PF_TRACE"), nullptr, 0) : nullptr;
         const int ns = n_seq - s0 < P2_MAX_SEQ ? n_seq - s0 : P2_MAX_SEQ;
         p.n_seq = ns;
         p.d_env = dev ? env_d + s0 : nullptr;

@@ -1,0 +1,363 @@
+// Dense prefill attention, operands A in tensor memory (tcgen05.mma "TS" form): Q and P never touch smem.
+//
+// Why: the SS kernels (attn_prefill.cu, attn_prefill2.cu) are bound by SHARED-MEMORY bandwidth, not by the
+// tensor pipe, MUFU or L2 (profiles/README.md): per 128-key tile the tensor core re-reads Q (32 KB) and P
+// (32 KB) from smem besides K and V, the softmax writes P (32 KB) and TMA writes K/V (64 KB) - 224 KB per
+// 1024 MMA cycles against ~128 B/clk.  Here Q is stored to TMEM once (tcgen05.st) and P overwrites the
+// front of its own S buffer in TMEM as packed bf16, so smem only carries K and V (TMA in, tensor core out).
+//
+//   warps 0-7 : softmax; warps w and w+4 share TMEM lanes (tile rows) 32(w%4)..+31 and take 64 score columns
+//               each; P(j) is written back with tcgen05.st into columns [0,64) of S buffer j&1.
+//   warp 8    : MMA issue (warp-uniform control flow, elected lane): S = Q K^T  [d=S buf, a=Q tmem, b=K smem],
+//               O += P V [d=O, a=P tmem, b=V smem, MN-major].  In-order tensor pipe: PV(j) precedes QK(j+2),
+//               which is what makes the S/P aliasing safe.
+//   warp 9    : TMA producer, 3-stage rings of K and V tiles (128 keys x 128 dims, two SWIZZLE_128B panels).
+// TMEM (512 cols): S/P buf 0 [0,128), buf 1 [128,256), O [256,384), Q [384,448).
+#include <stdlib.h>
+
+#include "tcgen05_helpers.cuh"
+
+namespace svln {
+
+constexpr int P3_BM = 128, P3_BN = 128, P3_HD = 128;
+constexpr int P3_STAGES = 3;
+constexpr int P3_PANEL = 128 * 128;
+constexpr int P3_TILE = 2 * P3_PANEL;           // 32 KB
+constexpr int P3_SOFTMAX_WARPS = 8;
+constexpr int P3_THREADS = (P3_SOFTMAX_WARPS + 2) * 32;
+constexpr int P3_MAX_SEQ = 64;
+
+constexpr int S3_K = 0;
+constexpr int S3_V = S3_K + P3_STAGES * P3_TILE;
+constexpr int S3_BAR = S3_V + P3_STAGES * P3_TILE;   // 192 KB
+constexpr int S3_XCH = S3_BAR + 256;                 // float [2][2][128] row-max exchange
+constexpr int P3_SMEM = S3_XCH + 2 * 2 * 128 * 4;
+
+enum { B3_K_FULL = 0, B3_K_EMPTY = 3, B3_V_FULL = 6, B3_V_EMPTY = 9, B3_S_FULL = 12, B3_P_FULL = 14, B3_PV_DONE = 16,
+       B3_COUNT = 18 };
+
+struct Prefill3Params {
+    const __nv_bfloat16* q;
+    __nv_bfloat16* out;
+    int n_q_head, n_kv_head, n_layer, layer, max_len;
+    int n_seq;
+    float scale_log2;
+    const int32_t *d_env, *d_q_start, *d_n_q, *d_kv_len;
+    int32_t env[P3_MAX_SEQ], q_start[P3_MAX_SEQ], n_q[P3_MAX_SEQ], kv_len[P3_MAX_SEQ];
+    int32_t tile_start[P3_MAX_SEQ + 1];
+};
+
+// D[tmem] (+)= A[tmem] * B[smem]
+__device__ __forceinline__ void tc_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accum) : "memory");
+}
+
+__global__ void __launch_bounds__(P3_THREADS, 1)
+attn_prefill3_kernel(const __grid_constant__ CUtensorMap kv_map, const __grid_constant__ Prefill3Params p) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const uint32_t sbase = s2u(smem);
+    if ((sbase & 1023u) != 0) __trap();
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + S3_BAR + B3_COUNT * 8);
+    const uint32_t bar0 = sbase + S3_BAR;
+    auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int kvh = blockIdx.y;
+    const int g = p.n_q_head / p.n_kv_head;
+    const int gtile = (int)gridDim.x - 1 - (int)blockIdx.x;   // heaviest (latest rows) first
+    int b = 0;
+    while (b + 1 < p.n_seq && gtile >= p.tile_start[b + 1]) ++b;
+    const int mtile = gtile - p.tile_start[b];
+    const bool dev = p.d_env != nullptr;
+    const int nq = dev ? p.d_n_q[b] : p.n_q[b];
+    const int len = dev ? p.d_kv_len[b] : p.kv_len[b];
+    const int env = dev ? p.d_env[b] : p.env[b];
+    const int qs = dev ? p.d_q_start[b] : p.q_start[b];
+    const int rows_total = nq * g;
+    const int row0 = mtile * P3_BM;
+    const int rows_here = min(P3_BM, rows_total - row0);
+    const int tq_last = (row0 + rows_here - 1) / g;
+    const int kv_hi = len - nq + tq_last + 1;
+    const int n_tiles = (kv_hi + P3_BN - 1) / P3_BN;
+    const int plane_k = ((env * p.n_layer + p.layer) * 2 + 0) * p.n_kv_head + kvh;
+    const int plane_v = plane_k + p.n_kv_head;
+
+    if (tid == 0) {
+        for (int i = 0; i < 12; ++i) mbar_init(BAR(i), 1);
+        mbar_init(BAR(B3_S_FULL), 1); mbar_init(BAR(B3_S_FULL + 1), 1);
+        mbar_init(BAR(B3_P_FULL), P3_SOFTMAX_WARPS); mbar_init(BAR(B3_P_FULL + 1), P3_SOFTMAX_WARPS);
+        mbar_init(BAR(B3_PV_DONE), 1); mbar_init(BAR(B3_PV_DONE + 1), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(s2u(tmem_ptr_smem)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+    const uint32_t TM_S0 = tmem_base, TM_O = tmem_base + 256, TM_Q = tmem_base + 384;
+
+    // Q tile -> TMEM as the A operand: lane = row, 32-bit column c = dims (2c, 2c+1).  Softmax mapping:
+    // row 32*(warp%4)+lane, dims [64*half, 64*half+64) = columns [32*half, 32*half+32).
+    if (warp < P3_SOFTMAX_WARPS) {
+        const int r = (warp & 3) * 32 + lane, half = warp >> 2;
+        const int R = row0 + r;
+        uint32_t qv[32];
+        if (r < rows_here) {
+            const int tq = R / g, hg = R - tq * g;
+            const int4* src = reinterpret_cast<const int4*>(p.q + ((int64_t)(qs + tq) * p.n_q_head + kvh * g + hg) * P3_HD) + half * 8;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const int4 v = __ldg(src + c);
+                qv[c * 4 + 0] = v.x; qv[c * 4 + 1] = v.y; qv[c * 4 + 2] = v.z; qv[c * 4 + 3] = v.w;
+            }
+        } else {
+#pragma unroll
+            for (int c = 0; c < 32; ++c) qv[c] = 0u;
+        }
+        tmem_st32(TM_Q + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(half * 32), qv);
+        tmem_wait_st();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+
+    if (warp == P3_SOFTMAX_WARPS + 1) {
+        // ------------------------------------------------------------ TMA producer (uniform warp, elected lane)
+        if (elect_one()) asm volatile("prefetch.tensormap [%0];" ::"l"(&kv_map) : "memory");
+        for (int j = 0; j < n_tiles; ++j) {
+            const int st = j % P3_STAGES, u = j / P3_STAGES;
+            const int key0 = j * P3_BN;
+            mbar_wait(BAR(B3_K_EMPTY + st), (u & 1) ^ 1);
+            if (elect_one()) {
+                mbar_expect_tx(BAR(B3_K_FULL + st), P3_TILE);
+                tma_load_3d(sbase + S3_K + st * P3_TILE, &kv_map, BAR(B3_K_FULL + st), 0, key0, plane_k);
+                tma_load_3d(sbase + S3_K + st * P3_TILE + P3_PANEL, &kv_map, BAR(B3_K_FULL + st), 64, key0, plane_k);
+            }
+            mbar_wait(BAR(B3_V_EMPTY + st), (u & 1) ^ 1);
+            if (elect_one()) {
+                mbar_expect_tx(BAR(B3_V_FULL + st), P3_TILE);
+                tma_load_3d(sbase + S3_V + st * P3_TILE, &kv_map, BAR(B3_V_FULL + st), 0, key0, plane_v);
+                tma_load_3d(sbase + S3_V + st * P3_TILE + P3_PANEL, &kv_map, BAR(B3_V_FULL + st), 64, key0, plane_v);
+            }
+            __syncwarp();
+        }
+    } else if (warp == P3_SOFTMAX_WARPS) {
+        // ------------------------------------------------------------ MMA issuer (uniform warp, elected lane)
+        constexpr uint32_t IDESC_QK = umma_idesc(0, 128);
+        constexpr uint32_t IDESC_PV = umma_idesc(1, 128);
+        auto issue_qk = [&](int j) {
+            const int st = j % P3_STAGES, bf = j & 1;
+            mbar_wait(BAR(B3_K_FULL + st), (j / P3_STAGES) & 1);
+            tc_fence_after();
+            const uint32_t kb = sbase + S3_K + st * P3_TILE;
+            if (elect_one()) {
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks)   // 16 dims per step = 8 TMEM columns of Q; K: 4 steps per 64-dim panel
+                    tc_mma_ts(TM_S0 + bf * 128, TM_Q + ks * 8, umma_desc(kb + (ks >> 2) * P3_PANEL + (ks & 3) * 32, 16, 1024),
+                              IDESC_QK, ks > 0);
+                tc_commit(BAR(B3_S_FULL + bf));
+                tc_commit(BAR(B3_K_EMPTY + st));
+            }
+            __syncwarp();
+        };
+        // S buffer bf is rewritten by QK(j+2) only after PV(j) (which read P(j) from it) was ISSUED: the tensor
+        // pipe runs in order, so no extra barrier is needed; PV(j) itself waits for P_FULL(j), i.e. for every
+        // softmax thread to be done with S(j).
+        issue_qk(0);
+        for (int j = 0; j < n_tiles; ++j) {
+            if (j + 1 < n_tiles) issue_qk(j + 1);
+            const int st = j % P3_STAGES, bf = j & 1, ub = j >> 1;
+            mbar_wait(BAR(B3_P_FULL + bf), ub & 1);
+            mbar_wait(BAR(B3_V_FULL + st), (j / P3_STAGES) & 1);
+            tc_fence_after();
+            const uint32_t vb = sbase + S3_V + st * P3_TILE;
+            if (elect_one()) {
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks)   // 16 keys per step = 8 TMEM columns of P; V: 16 rows x 128 B per step
+                    tc_mma_ts(TM_O, TM_S0 + bf * 128 + ks * 8, umma_desc(vb + ks * 2048, P3_PANEL, 1024), IDESC_PV,
+                              (j > 0 || ks > 0));
+                tc_commit(BAR(B3_V_EMPTY + st));
+                tc_commit(BAR(B3_PV_DONE + bf));
+            }
+            __syncwarp();
+        }
+    } else {
+        // ------------------------------------------------------------ softmax warps
+        const int r = (warp & 3) * 32 + lane;
+        const int half = warp >> 2;
+        const int R = row0 + r;
+        const bool row_valid = r < rows_here;
+        const int tq = row_valid ? R / g : 0;
+        const int hg = row_valid ? R - tq * g : 0;
+        const int lim = row_valid ? len - nq + tq + 1 : 0;
+        const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+        const uint32_t xch = sbase + S3_XCH;
+        const int pair_bar = 1 + (warp & 3);
+        float m_used = -INFINITY, l_sum = 0.f;
+        for (int j = 0; j < n_tiles; ++j) {
+            const int bf = j & 1, ub = j >> 1;
+            mbar_wait(BAR(B3_S_FULL + bf), ub & 1);
+            tc_fence_after();
+            uint32_t sv[2][32];
+            const uint32_t sbuf = TM_S0 + bf * 128 + lane_base;
+            tmem_ld32(sbuf + half * 64, sv[0]);
+            tmem_ld32(sbuf + half * 64 + 32, sv[1]);
+            tmem_wait_ld();
+            const int key0 = j * P3_BN + half * 64;
+            float mx = -INFINITY;
+            if (key0 + 64 > lim) {
+#pragma unroll
+                for (int c = 0; c < 2; ++c)
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) {
+                        if (key0 + c * 32 + e >= lim) sv[c][e] = 0xFF800000u;
+                        mx = fmaxf(mx, __uint_as_float(sv[c][e]));
+                    }
+            } else {
+#pragma unroll
+                for (int c = 0; c < 2; ++c)
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) mx = fmaxf(mx, __uint_as_float(sv[c][e]));
+            }
+            sts32f(xch + ((bf * 2 + half) * 128 + r) * 4, mx);
+            // pair barrier: (a) row max exchange, (b) both halves have their S(j) in registers, so P(j) may now
+            // overwrite columns [0,64) of this S buffer
+            asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+            mx = fmaxf(mx, lds32f(xch + ((bf * 2 + (half ^ 1)) * 128 + r) * 4)) * p.scale_log2;
+            float alpha = 1.f;
+            bool rescale = false;
+            if (mx > m_used + 8.0f || (m_used == -INFINITY && mx != -INFINITY)) {   // lazy rescale (factor 2^8)
+                alpha = m_used == -INFINITY ? 0.f : exp2f(m_used - mx);
+                m_used = mx;
+                rescale = j > 0;
+            }
+            const float neg_m = m_used == -INFINITY ? 0.f : -m_used;
+            l_sum *= alpha;
+            if (__any_sync(0xffffffffu, rescale)) {
+                mbar_wait(BAR(B3_PV_DONE + (bf ^ 1)), ((j - 1) >> 1) & 1);   // O quiescent: PV(j-1) done
+                tc_fence_after();
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    uint32_t ov[32];
+                    tmem_ld32(TM_O + lane_base + half * 64 + c * 32, ov);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) ov[e] = __float_as_uint(__uint_as_float(ov[e]) * alpha);
+                    tmem_st32(TM_O + lane_base + half * 64 + c * 32, ov);
+                }
+            }
+            // P = exp2(S*scale - m) -> packed bf16x2 -> TMEM columns [32*half, 32*half+32) of this S buffer
+            uint32_t pv[32];
+            float psum = 0.f;
+#pragma unroll
+            for (int c = 0; c < 2; ++c)
+#pragma unroll
+                for (int e = 0; e < 16; ++e) {
+                    const float p0 = ex2_approx(fmaf(__uint_as_float(sv[c][2 * e]), p.scale_log2, neg_m));
+                    const float p1 = ex2_approx(fmaf(__uint_as_float(sv[c][2 * e + 1]), p.scale_log2, neg_m));
+                    psum += p0 + p1;
+                    pv[c * 16 + e] = pack2_bf16(p0, p1);
+                }
+            l_sum += psum;
+            tmem_st32(TM_S0 + bf * 128 + lane_base + half * 32, pv);
+            tmem_wait_st();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(BAR(B3_P_FULL + bf));
+        }
+        // epilogue
+        asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+        sts32f(xch + (half * 128 + r) * 4, l_sum);
+        asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+        const float l_tot = l_sum + lds32f(xch + ((half ^ 1) * 128 + r) * 4);
+        mbar_wait(BAR(B3_PV_DONE + ((n_tiles - 1) & 1)), ((n_tiles - 1) >> 1) & 1);
+        tc_fence_after();
+        const float inv_l = l_tot > 0.f ? 1.0f / l_tot : 0.f;
+        __nv_bfloat16* orow = p.out + ((int64_t)(qs + tq) * p.n_q_head + kvh * g + hg) * P3_HD + half * 64;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            uint32_t ov[32];
+            tmem_ld32(TM_O + lane_base + half * 64 + c * 32, ov);
+            tmem_wait_ld();
+            if (row_valid) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    uint32_t w[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        w[e] = pack2_bf16(__uint_as_float(ov[q * 8 + 2 * e]) * inv_l, __uint_as_float(ov[q * 8 + 2 * e + 1]) * inv_l);
+                    *reinterpret_cast<int4*>(orow + c * 32 + q * 8) = make_int4(w[0], w[1], w[2], w[3]);
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+    }
+}
+
+int prefill3_launch(const svln_kv_arena* arena, int layer, const void* q, int n_q_head, const int32_t* env_h,
+                    const int32_t* q_start_h, const int32_t* n_q_h, const int32_t* kv_len_h, const int32_t* env_d,
+                    const int32_t* q_start_d, const int32_t* n_q_d, const int32_t* kv_len_d, int n_seq, float scale,
+                    void* out, svln_stream_t stream, const char* who) {
+    const bool dev = env_d != nullptr;
+    CUtensorMap map;
+    int rc = get_kv_map(arena, P3_BN, &map);
+    if (rc) return rc;
+    static bool attr_set = false;
+    if (!attr_set) {
+        SVLN_CUDA(cudaFuncSetAttribute(attn_prefill3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P3_SMEM));
+        attr_set = true;
+    }
+    const int g = n_q_head / arena->n_kv_head;
+    for (int s0 = 0; s0 < n_seq; s0 += P3_MAX_SEQ) {
+        Prefill3Params p;
+        p.q = (const __nv_bfloat16*)q;
+        p.out = (__nv_bfloat16*)out;
+        p.n_q_head = n_q_head; p.n_kv_head = arena->n_kv_head; p.n_layer = arena->n_layer; p.layer = layer;
+        p.max_len = arena->max_len;
+        p.scale_log2 = scale * 1.4426950408889634f;
+        const int ns = n_seq - s0 < P3_MAX_SEQ ? n_seq - s0 : P3_MAX_SEQ;
+        p.n_seq = ns;
+        p.d_env = dev ? env_d + s0 : nullptr;
+        p.d_q_start = dev ? q_start_d + s0 : nullptr;
+        p.d_n_q = dev ? n_q_d + s0 : nullptr;
+        p.d_kv_len = dev ? kv_len_d + s0 : nullptr;
+        int tiles = 0;
+        for (int i = 0; i < P3_MAX_SEQ; ++i) {
+            if (i < ns) {
+                const int bb = s0 + i;
+                SVLN_REQUIRE(n_q_h[bb] >= 1 && n_q_h[bb] <= arena->max_len, SVLN_ERR_INVALID, "%s: bad n_q=%d", who, n_q_h[bb]);
+                if (!dev) {
+                    SVLN_REQUIRE(env_h[bb] >= 0 && env_h[bb] < arena->n_env, SVLN_ERR_INVALID, "%s: env %d out of range", who, env_h[bb]);
+                    SVLN_REQUIRE(kv_len_h[bb] >= n_q_h[bb] && kv_len_h[bb] <= arena->max_len, SVLN_ERR_INVALID,
+                                 "%s: bad lengths n_q=%d kv_len=%d", who, n_q_h[bb], kv_len_h[bb]);
+                }
+                p.env[i] = dev ? 0 : env_h[bb]; p.q_start[i] = dev ? 0 : q_start_h[bb]; p.kv_len[i] = dev ? 0 : kv_len_h[bb];
+                p.n_q[i] = n_q_h[bb];
+                p.tile_start[i] = tiles;
+                tiles += (n_q_h[bb] * g + P3_BM - 1) / P3_BM;
+            } else {
+                p.env[i] = p.q_start[i] = p.n_q[i] = p.kv_len[i] = 0;
+                p.tile_start[i] = tiles;
+            }
+        }
+        p.tile_start[P3_MAX_SEQ] = tiles;
+        dim3 grid(tiles, arena->n_kv_head);
+        attn_prefill3_kernel<<<grid, P3_THREADS, P3_SMEM, (cudaStream_t)stream>>>(map, p);
+        rc = check_launch("attn_prefill3_kernel");
+        if (rc) return rc;
+    }
+    return SVLN_OK;
+}
+
+}  // namespace svln

@@ -10,6 +10,13 @@ namespace svln {
 // ---------------------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t s2u(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// one lane of a converged warp (warp-uniform control flow stays uniform for the compiler)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
@@ -112,6 +119,11 @@ __host__ __device__ constexpr uint32_t umma_idesc(int b_mn_major, uint32_t n = 1
 // host side (attn_prefill.cu / attn_prefill2.cu)
 int get_kv_map(const svln_kv_arena* a, int box_rows, CUtensorMap* out);
 int prefill2_launch(const svln_kv_arena* arena, int layer, const void* q, int n_q_head, const int32_t* env_h,
+                    const int32_t* q_start_h, const int32_t* n_q_h, const int32_t* kv_len_h, const int32_t* env_d,
+                    const int32_t* q_start_d, const int32_t* n_q_d, const int32_t* kv_len_d, int n_seq, float scale,
+                    void* out, svln_stream_t stream, const char* who);
+
+int prefill3_launch(const svln_kv_arena* arena, int layer, const void* q, int n_q_head, const int32_t* env_h,
                     const int32_t* q_start_h, const int32_t* n_q_h, const int32_t* kv_len_h, const int32_t* env_d,
                     const int32_t* q_start_d, const int32_t* n_q_d, const int32_t* kv_len_d, int n_seq, float scale,
                     void* out, svln_stream_t stream, const char* who);
