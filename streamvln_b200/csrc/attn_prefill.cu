@@ -387,7 +387,7 @@ static int prefill_launch(const svln_kv_arena* arena, int layer, const void* q, 
     const bool dev = env_d != nullptr;
     SVLN_REQUIRE(dev ? (q_start_d && n_q_d && kv_len_d) : (env_h && q_start_h && kv_len_h), SVLN_ERR_INVALID,
                  "%s: null descriptor array", who);
-    static const int version = getenv("SVLN_PF_V") ? atoi(getenv("SVLN_PF_V")) : 4;
+    static const int version = getenv("SVLN_PF_V") ? atoi(getenv("SVLN_PF_V")) : 5;  // 3: SS 128 rows, 4: SS 256 rows, 5: TS 128 rows (default)
     if (version >= 5)  // Q and P in tensor memory (TS-form MMAs): shared memory only carries K and V
         return prefill3_launch(arena, layer, q, n_q_head, env_h, q_start_h, n_q_h, kv_len_h, env_d, q_start_d, n_q_d, kv_len_d,
                                n_seq, scale, out, stream, who);
