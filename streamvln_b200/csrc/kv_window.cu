@@ -97,7 +97,7 @@ kv_append_rope_kernel(svln_kv_arena arena, int layer, const int4* __restrict__ q
 // src_row is strictly increasing with src >= dst, a chunk's destination rows are never the
 // source of a later chunk, and the barrier orders this chunk's loads before its stores.
 // K rows are re-rotated by (dst - src) positions while they are in registers.
-constexpr int CR = 256;           // rows per chunk: 256 rows x 256 B = 64 KB in flight per CTA
+constexpr int CR = 128;           // rows per chunk: 128 rows x 256 B = 32 KB in flight per CTA, 3 CTAs per SM
 constexpr int CQ = CR * 16 / 256; // int4 per thread per chunk (16)
 
 // rotate an 8-element (lo, hi) pair of fp32-expanded bf16 chunks by angle table row m:
@@ -127,7 +127,7 @@ __device__ __forceinline__ void rerotate8(int4& lo, int4& hi, const float* __res
     }
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 kv_compact_kernel(svln_kv_arena arena, const int32_t* __restrict__ job_env,
                   const int32_t* __restrict__ first_row, const int32_t* __restrict__ new_len,
                   const int32_t* __restrict__ src_row, int rerotate, const float* __restrict__ cos_delta,
