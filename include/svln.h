@@ -233,6 +233,11 @@ int svln_add_rmsnorm(void* x, const void* r, const void* weight, int64_t n_rows,
 /* gate_up [n_rows, 2*inter] bf16 (gate then up) -> out [n_rows, inter] = silu(gate)*up */
 int svln_swiglu(const void* gate_up, int64_t n_rows, int inter, void* out,
                 svln_stream_t stream);
+/* Weight-streaming GEMV for the decode of 1..4 streams: out[m,n] = sum_k x[m,k] * W[n,k] (+ bias[n]); W [N,K] and
+ * x [M,K] bf16 row-major, fp32 accumulation, out [M,N] bf16 (or fp32 when out_is_f32, for the lm_head logits).
+ * The Qwen2 linears at M = 1 are pure weight streaming; larger M are GEMMs and stay cuBLAS. */
+int svln_gemv(const void* W, const void* x, const void* bias, void* out, int M, int N, int K,
+              int out_is_f32, svln_stream_t stream);
 /* argmax over fp32 view of bf16/f32 logits rows; ties -> lowest index (torch.argmax). */
 int svln_argmax(const void* logits, int is_f32, int64_t n_rows, int64_t vocab,
                 int64_t* out_idx, svln_stream_t stream);

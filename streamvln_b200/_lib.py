@@ -74,6 +74,7 @@ PROTOTYPES = {
     "svln_rmsnorm": (_i, [_vp, _vp, _i64, _i, _f, _vp, _vp]),
     "svln_add_rmsnorm": (_i, [_vp, _vp, _vp, _i64, _i, _f, _vp, _vp]),
     "svln_swiglu": (_i, [_vp, _i64, _i, _vp, _vp]),
+    "svln_gemv": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "svln_argmax": (_i, [_vp, _i, _i64, _i64, _vp, _vp]),
 }
 

@@ -145,6 +145,7 @@ class Qwen2Engine:
         # SVLN_NO_GRAPH=1 launches everything eagerly (ncu cannot profile kernels issued during stream capture)
         self.use_graphs = os.environ.get("SVLN_NO_GRAPH", "0") != "1"
         self.use_prefill_graph = self.use_graphs
+        self.use_gemv = os.environ.get("SVLN_NO_GEMV", "0") != "1"
         self._pgraphs: Dict[tuple, "_PrefillGraph"] = {}
         self._pseen: Dict[tuple, int] = {}
         self._prof_flops = 0.0
@@ -170,6 +171,21 @@ class Qwen2Engine:
         self.launches += 1
         return out
 
+    GEMV_MAX_M = 4
+
+    def _linear(self, x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, f32_out: bool = False) -> torch.Tensor:
+        """x [M,K] @ w[N,K]^T (+ bias).  M <= 4 (single-episode decode) streams the weights with svln_gemv; larger M are
+        GEMMs and go to cuBLAS."""
+        M = x.shape[0]
+        if M <= self.GEMV_MAX_M and self.use_gemv:
+            out = torch.empty(M, w.shape[0], dtype=torch.float32 if f32_out else torch.bfloat16, device=x.device)
+            check(self.lib.svln_gemv(ptr(w), ptr(x), ptr(bias), ptr(out), M, w.shape[0], w.shape[1], 1 if f32_out else 0,
+                                     cur_stream()))
+            self.launches += 1
+            return out
+        y = torch.addmm(bias, x, w.t()) if bias is not None else x @ w.t()
+        return y.float() if f32_out else y
+
     def argmax(self, logits: torch.Tensor) -> torch.Tensor:
         out = torch.empty(logits.shape[0], dtype=torch.int64, device=logits.device)
         check(self.lib.svln_argmax(ptr(logits), 1 if logits.dtype == torch.float32 else 0, logits.shape[0],
@@ -190,13 +206,13 @@ class Qwen2Engine:
         pending = None  # MLP output of the previous layer, added to h by the next fused add+norm
         for li, L in enumerate(self.w.layers):
             x = self._rmsnorm(h, L["ln1"]) if pending is None else self._add_rmsnorm(h, pending, L["ln1"])
-            qkv = torch.addmm(L["bqkv"], x, L["wqkv"].t())
+            qkv = self._linear(x, L["wqkv"], L["bqkv"])
             self.arena.append_rope(li, qkv, H, tok_env, tok_pos, q_rot)
             self.launches += 1
             attn(li, q_rot, attn_out)
-            o = attn_out @ L["wo"].t()
+            o = self._linear(attn_out, L["wo"])
             x = self._add_rmsnorm(h, o, L["ln2"])
-            pending = self._swiglu(x @ L["wgu"].t()) @ L["wd"].t()
+            pending = self._linear(self._swiglu(self._linear(x, L["wgu"])), L["wd"])
         return h, pending
 
     def forward(self, h: torch.Tensor, chunks: Sequence[Chunk], last_only: bool = True) -> torch.Tensor:
@@ -267,7 +283,7 @@ class Qwen2Engine:
             rows64 = rows.to(torch.int64)
             h, pending = h.index_select(0, rows64), pending.index_select(0, rows64)
         x = self._add_rmsnorm(h, pending, self.w.final_norm)
-        return (x @ self.w.lm_head.t()).float()
+        return self._linear(x, self.w.lm_head, None, f32_out=True)
 
     # ------------------------------------------------------------------ greedy generation
     @torch.no_grad()
@@ -330,8 +346,7 @@ class Qwen2Engine:
             self.launches += 2
         h, pending = self._layers(h, state.seq_env, state.tok_pos, attn)
         x = self._add_rmsnorm(h, pending, self.w.final_norm)
-        logits = (x @ self.w.lm_head.t()).float()
-        return self.argmax(logits)
+        return self.argmax(self._linear(x, self.w.lm_head, None, f32_out=True))
 
 
 class _DecodeState:

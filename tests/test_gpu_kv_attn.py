@@ -254,3 +254,26 @@ def test_fused_ops(svln_lib, cuda):
     lb = logits.bfloat16()
     _lib.check(lib.svln_argmax(lb.data_ptr(), 0, 3, 152064, idx.data_ptr(), st))
     assert torch.equal(idx, lb.float().argmax(-1))
+
+
+def test_gemv_matches_linear(svln_lib, cuda):
+    """svln_gemv == F.linear in bf16 (fp32 accumulation, single rounding) within bf16 tolerance, for the Qwen2-7B
+    layer shapes and M = 1..4."""
+    from streamvln_b200 import _lib
+
+    lib = svln_lib
+    g = torch.Generator().manual_seed(11)
+    for N, K in ((4608, 3584), (3584, 3584), (2 * 18944, 3584), (3584, 18944), (1000, 256)):
+        W = (torch.randn(N, K, generator=g) * 0.02).bfloat16().to(cuda)
+        bias = (torch.randn(N, generator=g) * 0.02).bfloat16().to(cuda)
+        for M in (1, 2, 3, 4):
+            x = torch.randn(M, K, generator=g).bfloat16().to(cuda)
+            for b in (None, bias):
+                for f32 in (0, 1):
+                    out = torch.empty(M, N, dtype=torch.float32 if f32 else torch.bfloat16, device=cuda)
+                    _lib.check(lib.svln_gemv(W.data_ptr(), x.data_ptr(), None if b is None else b.data_ptr(), out.data_ptr(),
+                                             M, N, K, f32, _lib.cur_stream()))
+                    want = x.double() @ W.double().t() + (0 if b is None else b.double())
+                    err = (out.double() - want).abs().max().item() / want.abs().max().item()
+                    assert err <= (1e-5 if f32 else 2 ** -8), (N, K, M, f32, err)
+    assert lib.svln_gemv(W.data_ptr(), x.data_ptr(), None, out.data_ptr(), 5, N, K, 0, None) == -34
