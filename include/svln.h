@@ -206,7 +206,9 @@ int svln_attn_decode(const svln_kv_arena* arena, int layer, const void* q, int n
                      const int32_t* kv_len, int n_seq, int max_n_q, int max_kv_len, float scale,
                      void* workspace, size_t workspace_bytes, void* out, svln_stream_t stream);
 
-/* Dense prefill attention on tcgen05 tensor cores with TMEM accumulators (any n_q[b] >= 1). */
+/* Dense prefill attention on tcgen05 tensor cores with TMEM accumulators (any n_q[b] >= 1).  `workspace`
+ * (svln_attn_workspace_bytes; may be NULL) lets small grids split the key range across CTAs (split-KV) and
+ * merge the partials, so a single-episode turn (48 CTAs) still fills the 148 SMs. */
 int svln_attn_prefill(const svln_kv_arena* arena, int layer, const void* q, int n_q_head,
                       const int32_t* seq_env_host, const int32_t* q_start_host,
                       const int32_t* n_q_host, const int32_t* kv_len_host, int n_seq,
@@ -219,7 +221,7 @@ int svln_attn_prefill(const svln_kv_arena* arena, int layer, const void* q, int 
 int svln_attn_prefill_dev(const svln_kv_arena* arena, int layer, const void* q, int n_q_head,
                           const int32_t* seq_env, const int32_t* q_start, const int32_t* n_q,
                           const int32_t* kv_len, const int32_t* n_q_host, int n_seq, float scale,
-                          void* out, svln_stream_t stream);
+                          void* workspace, size_t workspace_bytes, void* out, svln_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Small fused ops around the Qwen2 linears (which stay cuBLAS): HF Qwen2RMSNorm and the

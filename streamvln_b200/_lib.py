@@ -70,7 +70,7 @@ PROTOTYPES = {
                               _vp, _vp]),
     "svln_attn_prefill": (_i, [_arena_p, _i, _vp, _i, _vp, _vp, _vp, _vp, _i, _f, _vp, _sz, _vp,
                                _vp]),
-    "svln_attn_prefill_dev": (_i, [_arena_p, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _f, _vp, _vp]),
+    "svln_attn_prefill_dev": (_i, [_arena_p, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _f, _vp, _sz, _vp, _vp]),
     "svln_rmsnorm": (_i, [_vp, _vp, _i64, _i, _f, _vp, _vp]),
     "svln_add_rmsnorm": (_i, [_vp, _vp, _vp, _i64, _i, _f, _vp, _vp]),
     "svln_swiglu": (_i, [_vp, _i64, _i, _vp, _vp]),

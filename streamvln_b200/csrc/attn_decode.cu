@@ -342,7 +342,10 @@ size_t svln_attn_workspace_bytes(int n_q_rows_max, int n_q_head, int head_dim, i
     // decode partial slots: (groups x kv heads x splits) <= groups*Hkv + 4*SMs (see svln_attn_decode);
     // groups <= rows, Hkv <= n_q_head
     const size_t slots = (size_t)n_q_rows_max * n_q_head + 4 * 160 + 64;
-    return slots * DROWS * (HD + 2) * sizeof(float) + 1024;
+    const size_t decode = slots * DROWS * (HD + 2) * sizeof(float) + 1024;
+    // split-KV prefill partials: up to 2 x SM-count slots of [128 rows][128 dims + 2] fp32
+    const size_t prefill = (size_t)2 * 160 * 128 * (HD + 2) * sizeof(float);
+    return decode > prefill ? decode : prefill;
 }
 
 int svln_attn_decode(const svln_kv_arena* arena, int layer, const void* q, int n_q_head, const int32_t* seq_env,

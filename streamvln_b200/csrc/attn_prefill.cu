@@ -375,7 +375,7 @@ int get_kv_map(const svln_kv_arena* a, int box_rows, CUtensorMap* out) {
 static int prefill_launch(const svln_kv_arena* arena, int layer, const void* q, int n_q_head, const int32_t* env_h,
                           const int32_t* q_start_h, const int32_t* n_q_h, const int32_t* kv_len_h, const int32_t* env_d,
                           const int32_t* q_start_d, const int32_t* n_q_d, const int32_t* kv_len_d, int n_seq, float scale,
-                          void* out, svln_stream_t stream, const char* who) {
+                          void* out, svln_stream_t stream, const char* who, void* workspace, size_t workspace_bytes) {
     SVLN_REQUIRE(arena && arena->base && arena->head_dim == 128, SVLN_ERR_INVALID, "%s: bad arena", who);
     SVLN_REQUIRE(layer >= 0 && layer < arena->n_layer, SVLN_ERR_INVALID, "%s: layer out of range", who);
     SVLN_REQUIRE(n_q_head > 0 && n_q_head % arena->n_kv_head == 0, SVLN_ERR_INVALID,
@@ -390,7 +390,7 @@ static int prefill_launch(const svln_kv_arena* arena, int layer, const void* q, 
     static const int version = getenv("SVLN_PF_V") ? atoi(getenv("SVLN_PF_V")) : 5;  // 3: SS 128 rows, 4: SS 256 rows, 5: TS 128 rows (default)
     if (version >= 5)  // Q and P in tensor memory (TS-form MMAs): shared memory only carries K and V
         return prefill3_launch(arena, layer, q, n_q_head, env_h, q_start_h, n_q_h, kv_len_h, env_d, q_start_d, n_q_d, kv_len_d,
-                               n_seq, scale, out, stream, who);
+                               n_seq, scale, out, stream, who, workspace, workspace_bytes);
     if (version == 4)  // 256 rows per CTA (two Q tiles share every K/V tile): half the L2->SM bytes per FLOP
         return prefill2_launch(arena, layer, q, n_q_head, env_h, q_start_h, n_q_h, kv_len_h, env_d, q_start_d, n_q_d, kv_len_d,
                                n_seq, scale, out, stream, who);
@@ -455,17 +455,16 @@ int svln_attn_prefill(const svln_kv_arena* arena, int layer, const void* q, int 
                       const int32_t* seq_env_host, const int32_t* q_start_host, const int32_t* n_q_host,
                       const int32_t* kv_len_host, int n_seq, float scale, void* workspace, size_t workspace_bytes,
                       void* out, svln_stream_t stream) {
-    (void)workspace; (void)workspace_bytes;
     return prefill_launch(arena, layer, q, n_q_head, seq_env_host, q_start_host, n_q_host, kv_len_host, nullptr, nullptr,
-                          nullptr, nullptr, n_seq, scale, out, stream, "svln_attn_prefill");
+                          nullptr, nullptr, n_seq, scale, out, stream, "svln_attn_prefill", workspace, workspace_bytes);
 }
 
 int svln_attn_prefill_dev(const svln_kv_arena* arena, int layer, const void* q, int n_q_head, const int32_t* seq_env,
                           const int32_t* q_start, const int32_t* n_q, const int32_t* kv_len, const int32_t* n_q_host,
-                          int n_seq, float scale, void* out, svln_stream_t stream) {
+                          int n_seq, float scale, void* workspace, size_t workspace_bytes, void* out, svln_stream_t stream) {
     SVLN_REQUIRE(seq_env, SVLN_ERR_INVALID, "svln_attn_prefill_dev: null seq_env");
     return prefill_launch(arena, layer, q, n_q_head, nullptr, nullptr, n_q_host, nullptr, seq_env, q_start, n_q, kv_len,
-                          n_seq, scale, out, stream, "svln_attn_prefill_dev");
+                          n_seq, scale, out, stream, "svln_attn_prefill_dev", workspace, workspace_bytes);
 }
 
 }  // extern "C"

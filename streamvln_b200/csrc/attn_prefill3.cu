@@ -45,6 +45,11 @@ struct Prefill3Params {
     const int32_t *d_env, *d_q_start, *d_n_q, *d_kv_len;
     int32_t env[P3_MAX_SEQ], q_start[P3_MAX_SEQ], n_q[P3_MAX_SEQ], kv_len[P3_MAX_SEQ];
     int32_t tile_start[P3_MAX_SEQ + 1];
+    // split-KV (small grids): gridDim.z CTAs share one M tile's key range; partials go to the workspace and
+    // attn_prefill3_combine_kernel merges them.  n_splits == 1 writes the final output directly.
+    int n_splits;
+    float* part_o;   // [slot][128 rows][128 dims] fp32, unnormalised
+    float* part_ml;  // [slot][128 rows][2] (reference max in log2 units, row sum)
 };
 
 // D[tmem] (+)= A[tmem] * B[smem]
@@ -81,7 +86,13 @@ attn_prefill3_kernel(const __grid_constant__ CUtensorMap kv_map, const __grid_co
     const int rows_here = min(P3_BM, rows_total - row0);
     const int tq_last = (row0 + rows_here - 1) / g;
     const int kv_hi = len - nq + tq_last + 1;
-    const int n_tiles = (kv_hi + P3_BN - 1) / P3_BN;
+    const int n_tiles_all = (kv_hi + P3_BN - 1) / P3_BN;
+    // this CTA's share of the key tiles (contiguous, balanced); may be empty for the last splits of short rows
+    const int split = blockIdx.z;
+    const int tile_lo = (int)(((int64_t)n_tiles_all * split) / p.n_splits);
+    const int tile_hi = (int)(((int64_t)n_tiles_all * (split + 1)) / p.n_splits);
+    const int n_tiles = tile_hi - tile_lo;
+    const int64_t slot = ((int64_t)gtile * gridDim.y + kvh) * p.n_splits + split;
     const int plane_k = ((env * p.n_layer + p.layer) * 2 + 0) * p.n_kv_head + kvh;
     const int plane_v = plane_k + p.n_kv_head;
 
@@ -132,7 +143,7 @@ attn_prefill3_kernel(const __grid_constant__ CUtensorMap kv_map, const __grid_co
         if (elect_one()) asm volatile("prefetch.tensormap [%0];" ::"l"(&kv_map) : "memory");
         for (int j = 0; j < n_tiles; ++j) {
             const int st = j % P3_STAGES, u = j / P3_STAGES;
-            const int key0 = j * P3_BN;
+            const int key0 = (tile_lo + j) * P3_BN;
             mbar_wait(BAR(B3_K_EMPTY + st), (u & 1) ^ 1);
             if (elect_one()) {
                 mbar_expect_tx(BAR(B3_K_FULL + st), P3_TILE);
@@ -169,7 +180,7 @@ attn_prefill3_kernel(const __grid_constant__ CUtensorMap kv_map, const __grid_co
         // S buffer bf is rewritten by QK(j+2) only after PV(j) (which read P(j) from it) was ISSUED: the tensor
         // pipe runs in order, so no extra barrier is needed; PV(j) itself waits for P_FULL(j), i.e. for every
         // softmax thread to be done with S(j).
-        issue_qk(0);
+        if (n_tiles > 0) issue_qk(0);
         for (int j = 0; j < n_tiles; ++j) {
             if (j + 1 < n_tiles) issue_qk(j + 1);
             const int st = j % P3_STAGES, bf = j & 1, ub = j >> 1;
@@ -209,7 +220,7 @@ attn_prefill3_kernel(const __grid_constant__ CUtensorMap kv_map, const __grid_co
             tmem_ld32(sbuf + half * 64, sv[0]);
             tmem_ld32(sbuf + half * 64 + 32, sv[1]);
             tmem_wait_ld();
-            const int key0 = j * P3_BN + half * 64;
+            const int key0 = (tile_lo + j) * P3_BN + half * 64;
             float mx = -INFINITY;
             if (key0 + 64 > lim) {
 #pragma unroll
@@ -276,23 +287,45 @@ attn_prefill3_kernel(const __grid_constant__ CUtensorMap kv_map, const __grid_co
         sts32f(xch + (half * 128 + r) * 4, l_sum);
         asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
         const float l_tot = l_sum + lds32f(xch + ((half ^ 1) * 128 + r) * 4);
-        mbar_wait(BAR(B3_PV_DONE + ((n_tiles - 1) & 1)), ((n_tiles - 1) >> 1) & 1);
-        tc_fence_after();
-        const float inv_l = l_tot > 0.f ? 1.0f / l_tot : 0.f;
-        __nv_bfloat16* orow = p.out + ((int64_t)(qs + tq) * p.n_q_head + kvh * g + hg) * P3_HD + half * 64;
+        if (n_tiles > 0) {
+            mbar_wait(BAR(B3_PV_DONE + ((n_tiles - 1) & 1)), ((n_tiles - 1) >> 1) & 1);
+            tc_fence_after();
+        }
+        if (p.n_splits == 1) {
+            const float inv_l = l_tot > 0.f ? 1.0f / l_tot : 0.f;
+            __nv_bfloat16* orow = p.out + ((int64_t)(qs + tq) * p.n_q_head + kvh * g + hg) * P3_HD + half * 64;
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-            uint32_t ov[32];
-            tmem_ld32(TM_O + lane_base + half * 64 + c * 32, ov);
-            tmem_wait_ld();
-            if (row_valid) {
+            for (int c = 0; c < 2; ++c) {
+                uint32_t ov[32];
+                tmem_ld32(TM_O + lane_base + half * 64 + c * 32, ov);
+                tmem_wait_ld();
+                if (row_valid) {
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    uint32_t w[4];
+                    for (int q = 0; q < 4; ++q) {
+                        uint32_t w[4];
 #pragma unroll
-                    for (int e = 0; e < 4; ++e)
-                        w[e] = pack2_bf16(__uint_as_float(ov[q * 8 + 2 * e]) * inv_l, __uint_as_float(ov[q * 8 + 2 * e + 1]) * inv_l);
-                    *reinterpret_cast<int4*>(orow + c * 32 + q * 8) = make_int4(w[0], w[1], w[2], w[3]);
+                        for (int e = 0; e < 4; ++e)
+                            w[e] = pack2_bf16(__uint_as_float(ov[q * 8 + 2 * e]) * inv_l, __uint_as_float(ov[q * 8 + 2 * e + 1]) * inv_l);
+                        *reinterpret_cast<int4*>(orow + c * 32 + q * 8) = make_int4(w[0], w[1], w[2], w[3]);
+                    }
+                }
+            }
+        } else {
+            // partial: unnormalised O, reference max and row sum of this key range (empty range: m = -inf, l = 0)
+            float* po = p.part_o + (slot * P3_BM + r) * P3_HD + half * 64;
+            if (half == 0) {
+                p.part_ml[(slot * P3_BM + r) * 2 + 0] = n_tiles > 0 ? m_used : -INFINITY;
+                p.part_ml[(slot * P3_BM + r) * 2 + 1] = n_tiles > 0 ? l_tot : 0.f;
+            }
+            if (n_tiles > 0) {
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    uint32_t ov[32];
+                    tmem_ld32(TM_O + lane_base + half * 64 + c * 32, ov);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int q = 0; q < 8; ++q)
+                        *reinterpret_cast<int4*>(po + c * 32 + q * 4) = make_int4(ov[q * 4], ov[q * 4 + 1], ov[q * 4 + 2], ov[q * 4 + 3]);
                 }
             }
         }
@@ -305,10 +338,50 @@ attn_prefill3_kernel(const __grid_constant__ CUtensorMap kv_map, const __grid_co
     }
 }
 
+// merge the split-KV partials of one (M tile, kv head): one warp per row, lanes over dims (4 floats each)
+__global__ void __launch_bounds__(256)
+attn_prefill3_combine_kernel(const __grid_constant__ Prefill3Params p) {
+    const int gtile = blockIdx.x, kvh = blockIdx.y;
+    const int g = p.n_q_head / p.n_kv_head;
+    int b = 0;
+    while (b + 1 < p.n_seq && gtile >= p.tile_start[b + 1]) ++b;
+    const int mtile = gtile - p.tile_start[b];
+    const bool dev = p.d_env != nullptr;
+    const int nq = dev ? p.d_n_q[b] : p.n_q[b];
+    const int qs = dev ? p.d_q_start[b] : p.q_start[b];
+    const int rows_total = nq * g;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t slot0 = ((int64_t)gtile * gridDim.y + kvh) * p.n_splits;
+    for (int r = warp; r < P3_BM; r += 8) {
+        const int R = mtile * P3_BM + r;
+        if (R >= rows_total) break;
+        float m = -INFINITY;
+        for (int s = 0; s < p.n_splits; ++s) m = fmaxf(m, p.part_ml[((slot0 + s) * P3_BM + r) * 2]);
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        float l = 0.f;
+        for (int s = 0; s < p.n_splits; ++s) {
+            const float ms = p.part_ml[((slot0 + s) * P3_BM + r) * 2];
+            if (ms == -INFINITY) continue;
+            const float w = exp2f(ms - m);
+            l += p.part_ml[((slot0 + s) * P3_BM + r) * 2 + 1] * w;
+            const float4 o = *reinterpret_cast<const float4*>(p.part_o + ((slot0 + s) * P3_BM + r) * P3_HD + lane * 4);
+            acc.x += o.x * w; acc.y += o.y * w; acc.z += o.z * w; acc.w += o.w * w;
+        }
+        const float inv_l = l > 0.f ? 1.0f / l : 0.f;
+        const int tq = R / g, hg = R - tq * g;
+        uint2 o2;
+        o2.x = pack2_bf16(acc.x * inv_l, acc.y * inv_l);
+        o2.y = pack2_bf16(acc.z * inv_l, acc.w * inv_l);
+        *reinterpret_cast<uint2*>(p.out + ((int64_t)(qs + tq) * p.n_q_head + kvh * g + hg) * P3_HD + lane * 4) = o2;
+    }
+}
+
+size_t prefill3_workspace_bytes(int64_t n_slots) { return (size_t)n_slots * P3_BM * (P3_HD + 2) * sizeof(float); }
+
 int prefill3_launch(const svln_kv_arena* arena, int layer, const void* q, int n_q_head, const int32_t* env_h,
                     const int32_t* q_start_h, const int32_t* n_q_h, const int32_t* kv_len_h, const int32_t* env_d,
                     const int32_t* q_start_d, const int32_t* n_q_d, const int32_t* kv_len_d, int n_seq, float scale,
-                    void* out, svln_stream_t stream, const char* who) {
+                    void* out, svln_stream_t stream, const char* who, void* workspace, size_t workspace_bytes) {
     const bool dev = env_d != nullptr;
     CUtensorMap map;
     int rc = get_kv_map(arena, P3_BN, &map);
@@ -352,8 +425,23 @@ int prefill3_launch(const svln_kv_arena* arena, int layer, const void* q, int n_
             }
         }
         p.tile_start[P3_MAX_SEQ] = tiles;
-        dim3 grid(tiles, arena->n_kv_head);
+        // split the key range when the grid cannot fill the GPU (single-episode turns: 12 M tiles x 4 kv heads)
+        const int ctas = tiles * arena->n_kv_head;
+        int n_splits = 1;
+        if (workspace && ctas < sm_count()) {
+            n_splits = (sm_count() + ctas - 1) / ctas;
+            if (n_splits > 8) n_splits = 8;
+            while (n_splits > 1 && prefill3_workspace_bytes((int64_t)ctas * n_splits) > workspace_bytes) --n_splits;
+        }
+        p.n_splits = n_splits;
+        p.part_o = (float*)workspace;
+        p.part_ml = p.part_o + (size_t)ctas * n_splits * P3_BM * P3_HD;
+        dim3 grid(tiles, arena->n_kv_head, n_splits);
         attn_prefill3_kernel<<<grid, P3_THREADS, P3_SMEM, (cudaStream_t)stream>>>(map, p);
+        if (n_splits > 1) {
+            dim3 cgrid(tiles, arena->n_kv_head);
+            attn_prefill3_combine_kernel<<<cgrid, 256, 0, (cudaStream_t)stream>>>(p);
+        }
         rc = check_launch("attn_prefill3_kernel");
         if (rc) return rc;
     }

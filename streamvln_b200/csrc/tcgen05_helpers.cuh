@@ -126,6 +126,6 @@ int prefill2_launch(const svln_kv_arena* arena, int layer, const void* q, int n_
 int prefill3_launch(const svln_kv_arena* arena, int layer, const void* q, int n_q_head, const int32_t* env_h,
                     const int32_t* q_start_h, const int32_t* n_q_h, const int32_t* kv_len_h, const int32_t* env_d,
                     const int32_t* q_start_d, const int32_t* n_q_d, const int32_t* kv_len_d, int n_seq, float scale,
-                    void* out, svln_stream_t stream, const char* who);
+                    void* out, svln_stream_t stream, const char* who, void* workspace, size_t workspace_bytes);
 
 }  // namespace svln

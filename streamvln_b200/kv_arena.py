@@ -102,15 +102,18 @@ class KvArena:
                      n_q: Sequence[int], kv_len: Sequence[int], scale: float, out: torch.Tensor) -> None:
         n = len(seq_env)
         arr = (C.c_int32 * n)
+        ws = self._workspace(min(q.shape[0], 4096), n_q_head)
         check(self.lib.svln_attn_prefill(self.ref, layer, ptr(q), n_q_head, arr(*seq_env), arr(*q_start), arr(*n_q),
-                                         arr(*kv_len), n, scale, None, 0, ptr(out), cur_stream()))
+                                         arr(*kv_len), n, scale, ptr(ws), ws.numel(), ptr(out), cur_stream()))
 
     def attn_prefill_dev(self, layer: int, q: torch.Tensor, n_q_head: int, desc: torch.Tensor, n_q_host: Sequence[int],
                          scale: float, out: torch.Tensor) -> None:
         """desc: device int32 [4, n_seq] = (env, q_start, n_q, kv_len) rows; graph-replayable."""
         n = len(n_q_host)
+        ws = self._workspace(min(q.shape[0], 4096), n_q_head)
         check(self.lib.svln_attn_prefill_dev(self.ref, layer, ptr(q), n_q_head, ptr(desc[0]), ptr(desc[1]), ptr(desc[2]),
-                                             ptr(desc[3]), (C.c_int32 * n)(*n_q_host), n, scale, ptr(out), cur_stream()))
+                                             ptr(desc[3]), (C.c_int32 * n)(*n_q_host), n, scale, ptr(ws), ws.numel(), ptr(out),
+                                             cur_stream()))
 
     # ---------------------------------------------------------------- views (tests, debugging)
     def plane(self, env: int, layer: int, kv: int) -> torch.Tensor:
