@@ -54,7 +54,10 @@ class KvArena:
         cd, sd = delta_rope_tables(max_len, head_dim, rope_theta)
         self.cos_delta, self.sin_delta = cd.to(self.device).contiguous(), sd.to(self.device).contiguous()
         self.lens = [0] * n_env  # host-side cache lengths (rows in use per stream)
-        self._attn_ws = None
+        # attention scratch (split-KV partials), allocated ONCE: captured CUDA graphs hold its address
+        self._attn_ws_rows = max(256, 4 * n_env)
+        self._attn_ws = torch.empty(self.lib.svln_attn_workspace_bytes(self._attn_ws_rows, 32, head_dim, max_len),
+                                    dtype=torch.uint8, device=self.device)
 
     # ---------------------------------------------------------------- append
     def append_rope(self, layer: int, qkv: torch.Tensor, n_q_head: int, tok_env: torch.Tensor,
@@ -82,10 +85,7 @@ class KvArena:
 
     # ---------------------------------------------------------------- attention
     def _workspace(self, n_rows: int, n_q_head: int) -> torch.Tensor:
-        need = self.lib.svln_attn_workspace_bytes(max(n_rows, 1), n_q_head, self.head_dim, self.max_len)
-        if self._attn_ws is None or self._attn_ws.numel() < need:
-            self._attn_ws = torch.empty(need, dtype=torch.uint8, device=self.device)
-        return self._attn_ws
+        return self._attn_ws  # the C side checks the size it needs against workspace_bytes and fails loudly
 
     def reserve_workspace(self, n_rows: int, n_q_head: int) -> None:
         self._workspace(n_rows, n_q_head)
@@ -102,7 +102,7 @@ class KvArena:
                      n_q: Sequence[int], kv_len: Sequence[int], scale: float, out: torch.Tensor) -> None:
         n = len(seq_env)
         arr = (C.c_int32 * n)
-        ws = self._workspace(min(q.shape[0], 4096), n_q_head)
+        ws = self._workspace(0, n_q_head)
         check(self.lib.svln_attn_prefill(self.ref, layer, ptr(q), n_q_head, arr(*seq_env), arr(*q_start), arr(*n_q),
                                          arr(*kv_len), n, scale, ptr(ws), ws.numel(), ptr(out), cur_stream()))
 
@@ -110,7 +110,7 @@ class KvArena:
                          scale: float, out: torch.Tensor) -> None:
         """desc: device int32 [4, n_seq] = (env, q_start, n_q, kv_len) rows; graph-replayable."""
         n = len(n_q_host)
-        ws = self._workspace(min(q.shape[0], 4096), n_q_head)
+        ws = self._workspace(0, n_q_head)
         check(self.lib.svln_attn_prefill_dev(self.ref, layer, ptr(q), n_q_head, ptr(desc[0]), ptr(desc[1]), ptr(desc[2]),
                                              ptr(desc[3]), (C.c_int32 * n)(*n_q_host), n, scale, ptr(ws), ws.numel(), ptr(out),
                                              cur_stream()))
