@@ -428,9 +428,13 @@ int prefill3_launch(const svln_kv_arena* arena, int layer, const void* q, int n_
         // split the key range when the grid cannot fill the GPU (single-episode turns: 12 M tiles x 4 kv heads)
         const int ctas = tiles * arena->n_kv_head;
         int n_splits = 1;
-        if (workspace && ctas < sm_count()) {
-            n_splits = (sm_count() + ctas - 1) / ctas;
-            if (n_splits > 8) n_splits = 8;
+        // measured on B200 (single-episode turn, 48 CTAs): splitting 2-3 ways does not pay - the fixed per-CTA cost
+        // (TMEM alloc, Q -> TMEM, pipeline fill) plus the combine pass outweighs the shorter key loops - so it is
+        // opt-in (SVLN_PF_SPLITS=n) rather than the default
+        static const int max_splits = getenv("SVLN_PF_SPLITS") ? atoi(getenv("SVLN_PF_SPLITS")) : 1;
+        if (workspace && ctas * 2 <= sm_count() && max_splits > 1) {
+            n_splits = sm_count() / ctas;   // one wave: never more CTAs than SMs (each CTA owns a whole SM)
+            if (n_splits > max_splits) n_splits = max_splits;
             while (n_splits > 1 && prefill3_workspace_bytes((int64_t)ctas * n_splits) > workspace_bytes) --n_splits;
         }
         p.n_splits = n_splits;
