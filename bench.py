@@ -185,15 +185,24 @@ def main_batched(a):
                               for f in frames_host]).to(device)
     live = list(range(E))
     instr = {i: INSTRUCTION for i in live}
+    geom_src = None
+    if a.mode == "slowfast":
+        from streamvln_b200 import synth
+
+        geom_src = [synth.make_stream(256, 14, 8, seed=1000 * rank + i, with_feat=False) for i in range(min(E, 8))]
 
     def turns(n, resident):
         for _ in range(n):
             for k in range(ENV_STEPS_PER_TURN):
                 s = ev.agents[0].step_id
+                geom = None
+                if geom_src is not None:
+                    geom = {i: dict(depth=geom_src[i % len(geom_src)]["depth"][s % 256], pose=geom_src[i % len(geom_src)]["pose"][s % 256],
+                                    intrinsic=geom_src[i % len(geom_src)]["intr"][0]) for i in live}
                 if resident:
-                    ev.step_all(live, None, instr, k == 0, None, {i: frames_dev[(s + i) % 16] for i in live} if k == 0 else None)
+                    ev.step_all(live, None, instr, k == 0, geom, {i: frames_dev[(s + i) % 16] for i in live} if k == 0 else None)
                 else:
-                    ev.step_all(live, {i: frames_host[(s + i) % 16] for i in live}, instr, k == 0)
+                    ev.step_all(live, {i: frames_host[(s + i) % 16] for i in live}, instr, k == 0, geom)
 
     def run(n, resident):
         if dist is not None:
