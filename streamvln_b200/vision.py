@@ -101,6 +101,36 @@ class VisionFrontEnd(torch.nn.Module):
         self._graphs: Dict[int, dict] = {}
         self._seen: Dict[int, int] = {}
 
+    @torch.no_grad()
+    def load_hf_state_dict(self, sd: Dict[str, torch.Tensor], prefix: str = "model.vision_tower.vision_tower.",
+                           projector_prefix: str = "model.mm_projector.") -> None:
+        """Load the tower + projector from a StreamVLN / LLaVA checkpoint's state dict (HF SigLIP names:
+        `{prefix}vision_model.encoder.layers.N.self_attn.q_proj.weight`, ...; projector `{projector_prefix}0.weight`,
+        `{projector_prefix}2.weight` for mlp2x_gelu).  q/k/v are fused row-wise; the patch-embedding conv becomes a
+        [D, 3*14*14] matrix (same (c, ky, kx) order as the conv weight).  Layers beyond `num_layers` (the dropped
+        27th) and the pooling head are ignored, as in siglip_encoder.py:570-571."""
+        dt, dev = self.patch_w.dtype, self.patch_w.device
+
+        def t(name):
+            return sd[prefix + "vision_model." + name].to(device=dev, dtype=dt)
+
+        self.patch_w.copy_(t("embeddings.patch_embedding.weight").reshape(self.cfg.hidden_size, -1))
+        self.patch_b.copy_(t("embeddings.patch_embedding.bias"))
+        self.pos.copy_(t("embeddings.position_embedding.weight"))
+        for i in range(self.cfg.num_layers):
+            L, e = self._layer(i), f"encoder.layers.{i}."
+            L["ln1_w"].copy_(t(e + "layer_norm1.weight")); L["ln1_b"].copy_(t(e + "layer_norm1.bias"))
+            L["wqkv"].copy_(torch.cat([t(e + f"self_attn.{n}_proj.weight") for n in "qkv"]))
+            L["bqkv"].copy_(torch.cat([t(e + f"self_attn.{n}_proj.bias") for n in "qkv"]))
+            L["wo"].copy_(t(e + "self_attn.out_proj.weight")); L["bo"].copy_(t(e + "self_attn.out_proj.bias"))
+            L["ln2_w"].copy_(t(e + "layer_norm2.weight")); L["ln2_b"].copy_(t(e + "layer_norm2.bias"))
+            L["w1"].copy_(t(e + "mlp.fc1.weight")); L["b1"].copy_(t(e + "mlp.fc1.bias"))
+            L["w2"].copy_(t(e + "mlp.fc2.weight")); L["b2"].copy_(t(e + "mlp.fc2.bias"))
+        if projector_prefix is not None and projector_prefix + "0.weight" in sd:
+            self.proj_w1.copy_(sd[projector_prefix + "0.weight"].to(dev, dt)); self.proj_b1.copy_(sd[projector_prefix + "0.bias"].to(dev, dt))
+            self.proj_w2.copy_(sd[projector_prefix + "2.weight"].to(dev, dt)); self.proj_b2.copy_(sd[projector_prefix + "2.bias"].to(dev, dt))
+        self._graphs.clear()
+
     # attribute access used by the reference's call sites (streamvln_agent.py:43)
     @property
     def num_patches_per_side(self) -> int:
