@@ -18,8 +18,8 @@ for _ in range(3):
 torch.cuda.synchronize()
 t = trace.cpu().view(4, 32, 8)
 base = int(t[t > 0].min())
-names = {0: "softmax t0: 0 start,1 S_FULL,2 ld+arrive,3 max done,4 PV_DONE(j-2),5 exp+store done,6 fence+arrive",
-         1: "softmax t1", 2: "MMA: 0 qk start,1 K_FULL,2 qk issued,3 V_FULL,4 P_FULL t0,5 P_FULL t1,6 pv issued", 3: "TMA: 0 start,1 K_EMPTY,2 V_EMPTY"}
+names = {0: "softmax half0: 0 start,1 S_FULL,2 ld+max done,3 exchange+rescale decided,4 exp done,5 P stored+arrive",
+         1: "softmax half1", 2: "MMA: 0 qk start,1 K_FULL,2 qk issued,3 P_FULL,4 V_FULL,5 pv issued", 3: "TMA: 0 start,1 K_EMPTY,2 V_EMPTY"}
 for role in range(4):
     print(names[role])
     for j in range(2, 14):

@@ -50,7 +50,24 @@ struct Prefill3Params {
     int n_splits;
     float* part_o;   // [slot][128 rows][128 dims] fp32, unnormalised
     float* part_ml;  // [slot][128 rows][2] (reference max in log2 units, row sum)
+    int debug;         // SVLN_PF_DEBUG bit 0: skip the MUFU.EX2 (bottleneck experiments only; results are wrong)
+    long long* trace;  // SVLN_PF_TRACE: clock64 stamps of one CTA (scripts/prefill_trace.py), else nullptr
 };
+
+// Instrumentation is compiled out unless the library is built with -DSVLN_PF_INSTRUMENT (it costs ~8 % of the
+// kernel's throughput even when disabled at run time).
+// trace layout: [role 0..3][tile 0..31][slot 0..7]; roles: 0 softmax warp 0, 1 softmax warp 4, 2 MMA warp, 3 TMA warp
+#ifndef SVLN_PF_INSTRUMENT
+#define P3_TRACE(role, tile, slot) do { } while (0)
+#define P3_NO_MUFU false
+#else
+#define P3_NO_MUFU ((p.debug & 1) != 0)
+#define P3_TRACE(role, tile, slot)                                                                           \
+    do {                                                                                                     \
+        if (p.trace && blockIdx.x == gridDim.x / 2 && blockIdx.y == 0 && blockIdx.z == 0 && (tile) < 32 && lane == 0) \
+            p.trace[((role) * 32 + (tile)) * 8 + (slot)] = clock64();                                        \
+    } while (0)
+#endif
 
 // D[tmem] (+)= A[tmem] * B[smem]
 __device__ __forceinline__ void tc_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accum) {
@@ -60,6 +77,27 @@ __device__ __forceinline__ void tc_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint
         ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accum) : "memory");
 }
 
+// CLUSTER = true: two CTAs (adjacent M tiles of the same sequence / kv head) form a cluster; each loads ONE 64-dim
+// panel of every K and V tile and TMA-multicasts it into both CTAs' shared memory, so every K/V byte leaves L2
+// once per 256 query rows instead of once per 128 (the 128-row kernel sits on the ~6.9 TB/s L2->SM ceiling).
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_3d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5}], [%2], %6;"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void tc_commit_mc(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask) : "memory");
+}
+
+template <bool CLUSTER>
 __global__ void __launch_bounds__(P3_THREADS, 1)
 attn_prefill3_kernel(const __grid_constant__ CUtensorMap kv_map, const __grid_constant__ Prefill3Params p) {
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -84,8 +122,12 @@ attn_prefill3_kernel(const __grid_constant__ CUtensorMap kv_map, const __grid_co
     const int rows_total = nq * g;
     const int row0 = mtile * P3_BM;
     const int rows_here = min(P3_BM, rows_total - row0);
-    const int tq_last = (row0 + rows_here - 1) / g;
+    // CLUSTER: both CTAs of a pair walk the key range of the pair's LAST valid row (tile counts are padded to even
+    // per sequence, so the partner is mtile ^ 1 of the same sequence; a padding tile has no valid rows)
+    const int pair_rows_end = CLUSTER ? min(rows_total, ((mtile | 1) + 1) * P3_BM) : row0 + rows_here;
+    const int tq_last = (pair_rows_end - 1) / g;
     const int kv_hi = len - nq + tq_last + 1;
+    const uint32_t crank = CLUSTER ? cluster_ctarank() : 0u;
     const int n_tiles_all = (kv_hi + P3_BN - 1) / P3_BN;
     // this CTA's share of the key tiles (contiguous, balanced); may be empty for the last splits of short rows
     const int split = blockIdx.z;
@@ -98,6 +140,8 @@ attn_prefill3_kernel(const __grid_constant__ CUtensorMap kv_map, const __grid_co
 
     if (tid == 0) {
         for (int i = 0; i < 12; ++i) mbar_init(BAR(i), 1);
+        if (CLUSTER)   // a stage is free only when BOTH CTAs' tensor cores are done with it
+            for (int i = 0; i < 3; ++i) { mbar_init(BAR(B3_K_EMPTY + i), 2); mbar_init(BAR(B3_V_EMPTY + i), 2); }
         mbar_init(BAR(B3_S_FULL), 1); mbar_init(BAR(B3_S_FULL + 1), 1);
         mbar_init(BAR(B3_P_FULL), P3_SOFTMAX_WARPS); mbar_init(BAR(B3_P_FULL + 1), P3_SOFTMAX_WARPS);
         mbar_init(BAR(B3_PV_DONE), 1); mbar_init(BAR(B3_PV_DONE + 1), 1);
@@ -109,6 +153,7 @@ attn_prefill3_kernel(const __grid_constant__ CUtensorMap kv_map, const __grid_co
     }
     tc_fence_before();
     __syncthreads();
+    if (CLUSTER) cluster_sync_all();   // the partner's barriers are initialised before anything is multicast into them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
     const uint32_t TM_S0 = tmem_base, TM_O = tmem_base + 256, TM_Q = tmem_base + 384;
@@ -144,17 +189,28 @@ attn_prefill3_kernel(const __grid_constant__ CUtensorMap kv_map, const __grid_co
         for (int j = 0; j < n_tiles; ++j) {
             const int st = j % P3_STAGES, u = j / P3_STAGES;
             const int key0 = (tile_lo + j) * P3_BN;
+            P3_TRACE(3, j, 0);
             mbar_wait(BAR(B3_K_EMPTY + st), (u & 1) ^ 1);
+            P3_TRACE(3, j, 1);
             if (elect_one()) {
-                mbar_expect_tx(BAR(B3_K_FULL + st), P3_TILE);
-                tma_load_3d(sbase + S3_K + st * P3_TILE, &kv_map, BAR(B3_K_FULL + st), 0, key0, plane_k);
-                tma_load_3d(sbase + S3_K + st * P3_TILE + P3_PANEL, &kv_map, BAR(B3_K_FULL + st), 64, key0, plane_k);
+                mbar_expect_tx(BAR(B3_K_FULL + st), P3_TILE);   // both panels land here: one from each CTA of the pair
+                if (CLUSTER) {
+                    tma_load_3d_mc(sbase + S3_K + st * P3_TILE + crank * P3_PANEL, &kv_map, BAR(B3_K_FULL + st), 64 * crank, key0, plane_k, 3);
+                } else {
+                    tma_load_3d(sbase + S3_K + st * P3_TILE, &kv_map, BAR(B3_K_FULL + st), 0, key0, plane_k);
+                    tma_load_3d(sbase + S3_K + st * P3_TILE + P3_PANEL, &kv_map, BAR(B3_K_FULL + st), 64, key0, plane_k);
+                }
             }
             mbar_wait(BAR(B3_V_EMPTY + st), (u & 1) ^ 1);
+            P3_TRACE(3, j, 2);
             if (elect_one()) {
                 mbar_expect_tx(BAR(B3_V_FULL + st), P3_TILE);
-                tma_load_3d(sbase + S3_V + st * P3_TILE, &kv_map, BAR(B3_V_FULL + st), 0, key0, plane_v);
-                tma_load_3d(sbase + S3_V + st * P3_TILE + P3_PANEL, &kv_map, BAR(B3_V_FULL + st), 64, key0, plane_v);
+                if (CLUSTER) {
+                    tma_load_3d_mc(sbase + S3_V + st * P3_TILE + crank * P3_PANEL, &kv_map, BAR(B3_V_FULL + st), 64 * crank, key0, plane_v, 3);
+                } else {
+                    tma_load_3d(sbase + S3_V + st * P3_TILE, &kv_map, BAR(B3_V_FULL + st), 0, key0, plane_v);
+                    tma_load_3d(sbase + S3_V + st * P3_TILE + P3_PANEL, &kv_map, BAR(B3_V_FULL + st), 64, key0, plane_v);
+                }
             }
             __syncwarp();
         }
@@ -164,7 +220,9 @@ attn_prefill3_kernel(const __grid_constant__ CUtensorMap kv_map, const __grid_co
         constexpr uint32_t IDESC_PV = umma_idesc(1, 128);
         auto issue_qk = [&](int j) {
             const int st = j % P3_STAGES, bf = j & 1;
+            P3_TRACE(2, j, 0);
             mbar_wait(BAR(B3_K_FULL + st), (j / P3_STAGES) & 1);
+            P3_TRACE(2, j, 1);
             tc_fence_after();
             const uint32_t kb = sbase + S3_K + st * P3_TILE;
             if (elect_one()) {
@@ -173,9 +231,10 @@ attn_prefill3_kernel(const __grid_constant__ CUtensorMap kv_map, const __grid_co
                     tc_mma_ts(TM_S0 + bf * 128, TM_Q + ks * 8, umma_desc(kb + (ks >> 2) * P3_PANEL + (ks & 3) * 32, 16, 1024),
                               IDESC_QK, ks > 0);
                 tc_commit(BAR(B3_S_FULL + bf));
-                tc_commit(BAR(B3_K_EMPTY + st));
+                if (CLUSTER) tc_commit_mc(BAR(B3_K_EMPTY + st), 3); else tc_commit(BAR(B3_K_EMPTY + st));
             }
             __syncwarp();
+            P3_TRACE(2, j, 2);
         };
         // S buffer bf is rewritten by QK(j+2) only after PV(j) (which read P(j) from it) was ISSUED: the tensor
         // pipe runs in order, so no extra barrier is needed; PV(j) itself waits for P_FULL(j), i.e. for every
@@ -185,7 +244,9 @@ attn_prefill3_kernel(const __grid_constant__ CUtensorMap kv_map, const __grid_co
             if (j + 1 < n_tiles) issue_qk(j + 1);
             const int st = j % P3_STAGES, bf = j & 1, ub = j >> 1;
             mbar_wait(BAR(B3_P_FULL + bf), ub & 1);
+            P3_TRACE(2, j, 3);
             mbar_wait(BAR(B3_V_FULL + st), (j / P3_STAGES) & 1);
+            P3_TRACE(2, j, 4);
             tc_fence_after();
             const uint32_t vb = sbase + S3_V + st * P3_TILE;
             if (elect_one()) {
@@ -193,10 +254,11 @@ attn_prefill3_kernel(const __grid_constant__ CUtensorMap kv_map, const __grid_co
                 for (int ks = 0; ks < 8; ++ks)   // 16 keys per step = 8 TMEM columns of P; V: 16 rows x 128 B per step
                     tc_mma_ts(TM_O, TM_S0 + bf * 128 + ks * 8, umma_desc(vb + ks * 2048, P3_PANEL, 1024), IDESC_PV,
                               (j > 0 || ks > 0));
-                tc_commit(BAR(B3_V_EMPTY + st));
+                if (CLUSTER) tc_commit_mc(BAR(B3_V_EMPTY + st), 3); else tc_commit(BAR(B3_V_EMPTY + st));
                 tc_commit(BAR(B3_PV_DONE + bf));
             }
             __syncwarp();
+            P3_TRACE(2, j, 5);
         }
     } else {
         // ------------------------------------------------------------ softmax warps
@@ -213,7 +275,11 @@ attn_prefill3_kernel(const __grid_constant__ CUtensorMap kv_map, const __grid_co
         float m_used = -INFINITY, l_sum = 0.f;
         for (int j = 0; j < n_tiles; ++j) {
             const int bf = j & 1, ub = j >> 1;
+            const int trole = (warp & 3) == 0 ? half : 99;
+            (void)trole;
+            if (trole < 2) P3_TRACE(trole, j, 0);
             mbar_wait(BAR(B3_S_FULL + bf), ub & 1);
+            if (trole < 2) P3_TRACE(trole, j, 1);
             tc_fence_after();
             uint32_t sv[2][32];
             const uint32_t sbuf = TM_S0 + bf * 128 + lane_base;
@@ -236,6 +302,7 @@ attn_prefill3_kernel(const __grid_constant__ CUtensorMap kv_map, const __grid_co
 #pragma unroll
                     for (int e = 0; e < 32; ++e) mx = fmaxf(mx, __uint_as_float(sv[c][e]));
             }
+            if (trole < 2) P3_TRACE(trole, j, 2);
             sts32f(xch + ((bf * 2 + half) * 128 + r) * 4, mx);
             // pair barrier: (a) row max exchange, (b) both halves have their S(j) in registers, so P(j) may now
             // overwrite columns [0,64) of this S buffer
@@ -250,6 +317,7 @@ attn_prefill3_kernel(const __grid_constant__ CUtensorMap kv_map, const __grid_co
             }
             const float neg_m = m_used == -INFINITY ? 0.f : -m_used;
             l_sum *= alpha;
+            if (trole < 2) P3_TRACE(trole, j, 3);
             if (__any_sync(0xffffffffu, rescale)) {
                 mbar_wait(BAR(B3_PV_DONE + (bf ^ 1)), ((j - 1) >> 1) & 1);   // O quiescent: PV(j-1) done
                 tc_fence_after();
@@ -270,17 +338,20 @@ attn_prefill3_kernel(const __grid_constant__ CUtensorMap kv_map, const __grid_co
             for (int c = 0; c < 2; ++c)
 #pragma unroll
                 for (int e = 0; e < 16; ++e) {
-                    const float p0 = ex2_approx(fmaf(__uint_as_float(sv[c][2 * e]), p.scale_log2, neg_m));
-                    const float p1 = ex2_approx(fmaf(__uint_as_float(sv[c][2 * e + 1]), p.scale_log2, neg_m));
+                    float p0 = fmaf(__uint_as_float(sv[c][2 * e]), p.scale_log2, neg_m);
+                    float p1 = fmaf(__uint_as_float(sv[c][2 * e + 1]), p.scale_log2, neg_m);
+                    if (!P3_NO_MUFU) { p0 = ex2_approx(p0); p1 = ex2_approx(p1); }
                     psum += p0 + p1;
                     pv[c * 16 + e] = pack2_bf16(p0, p1);
                 }
             l_sum += psum;
+            if (trole < 2) P3_TRACE(trole, j, 4);
             tmem_st32(TM_S0 + bf * 128 + lane_base + half * 32, pv);
             tmem_wait_st();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(BAR(B3_P_FULL + bf));
+            if (trole < 2) P3_TRACE(trole, j, 5);
         }
         // epilogue
         asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
@@ -332,6 +403,7 @@ attn_prefill3_kernel(const __grid_constant__ CUtensorMap kv_map, const __grid_co
         tc_fence_before();
     }
     __syncthreads();
+    if (CLUSTER) cluster_sync_all();   // neither CTA may exit while the partner can still multicast / commit into it
     if (warp == 0) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
@@ -388,9 +460,13 @@ int prefill3_launch(const svln_kv_arena* arena, int layer, const void* q, int n_
     if (rc) return rc;
     static bool attr_set = false;
     if (!attr_set) {
-        SVLN_CUDA(cudaFuncSetAttribute(attn_prefill3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P3_SMEM));
+        SVLN_CUDA(cudaFuncSetAttribute(attn_prefill3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, P3_SMEM));
+        SVLN_CUDA(cudaFuncSetAttribute(attn_prefill3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, P3_SMEM));
         attr_set = true;
     }
+    // measured on B200: the multicast pair is ~5 % SLOWER than the plain kernel at the 64-stream shapes (L2 already
+    // serves the repeated K/V tiles; the pair adds cluster barriers and lock-step) - opt-in via SVLN_PF_CLUSTER=1
+    static const int cluster_mode = getenv("SVLN_PF_CLUSTER") ? atoi(getenv("SVLN_PF_CLUSTER")) : 0;
     const int g = n_q_head / arena->n_kv_head;
     for (int s0 = 0; s0 < n_seq; s0 += P3_MAX_SEQ) {
         Prefill3Params p;
@@ -399,12 +475,18 @@ int prefill3_launch(const svln_kv_arena* arena, int layer, const void* q, int n_
         p.n_q_head = n_q_head; p.n_kv_head = arena->n_kv_head; p.n_layer = arena->n_layer; p.layer = layer;
         p.max_len = arena->max_len;
         p.scale_log2 = scale * 1.4426950408889634f;
+        p.debug = getenv("SVLN_PF_DEBUG") ? atoi(getenv("SVLN_PF_DEBUG")) : 0;
+        p.trace = getenv("SVLN_PF_TRACE") ? (long long*)strtoull(getenv("SVLN_PF_TRACE"), nullptr, 0) : nullptr;
         const int ns = n_seq - s0 < P3_MAX_SEQ ? n_seq - s0 : P3_MAX_SEQ;
         p.n_seq = ns;
         p.d_env = dev ? env_d + s0 : nullptr;
         p.d_q_start = dev ? q_start_d + s0 : nullptr;
         p.d_n_q = dev ? n_q_d + s0 : nullptr;
         p.d_kv_len = dev ? kv_len_d + s0 : nullptr;
+        // multicast pairs pay off once there are enough M tiles to fill the GPU; tiny launches keep the plain kernel
+        int raw_tiles = 0;
+        for (int i = 0; i < ns; ++i) raw_tiles += (n_q_h[s0 + i] * g + P3_BM - 1) / P3_BM;
+        const bool use_cluster = cluster_mode != 0 && raw_tiles * arena->n_kv_head >= sm_count();
         int tiles = 0;
         for (int i = 0; i < P3_MAX_SEQ; ++i) {
             if (i < ns) {
@@ -418,7 +500,9 @@ int prefill3_launch(const svln_kv_arena* arena, int layer, const void* q, int n_
                 p.env[i] = dev ? 0 : env_h[bb]; p.q_start[i] = dev ? 0 : q_start_h[bb]; p.kv_len[i] = dev ? 0 : kv_len_h[bb];
                 p.n_q[i] = n_q_h[bb];
                 p.tile_start[i] = tiles;
-                tiles += (n_q_h[bb] * g + P3_BM - 1) / P3_BM;
+                int nt = (n_q_h[bb] * g + P3_BM - 1) / P3_BM;
+                if (use_cluster) nt = (nt + 1) & ~1;   // pairs never straddle sequences
+                tiles += nt;
             } else {
                 p.env[i] = p.q_start[i] = p.n_q[i] = p.kv_len[i] = 0;
                 p.tile_start[i] = tiles;
@@ -432,7 +516,7 @@ int prefill3_launch(const svln_kv_arena* arena, int layer, const void* q, int n_
         // (TMEM alloc, Q -> TMEM, pipeline fill) plus the combine pass outweighs the shorter key loops - so it is
         // opt-in (SVLN_PF_SPLITS=n) rather than the default
         static const int max_splits = getenv("SVLN_PF_SPLITS") ? atoi(getenv("SVLN_PF_SPLITS")) : 1;
-        if (workspace && ctas * 2 <= sm_count() && max_splits > 1) {
+        if (!use_cluster && workspace && ctas * 2 <= sm_count() && max_splits > 1) {
             n_splits = sm_count() / ctas;   // one wave: never more CTAs than SMs (each CTA owns a whole SM)
             if (n_splits > max_splits) n_splits = max_splits;
             while (n_splits > 1 && prefill3_workspace_bytes((int64_t)ctas * n_splits) > workspace_bytes) --n_splits;
@@ -441,7 +525,21 @@ int prefill3_launch(const svln_kv_arena* arena, int layer, const void* q, int n_
         p.part_o = (float*)workspace;
         p.part_ml = p.part_o + (size_t)ctas * n_splits * P3_BM * P3_HD;
         dim3 grid(tiles, arena->n_kv_head, n_splits);
-        attn_prefill3_kernel<<<grid, P3_THREADS, P3_SMEM, (cudaStream_t)stream>>>(map, p);
+        if (use_cluster) {
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = grid;
+            cfg.blockDim = dim3(P3_THREADS);
+            cfg.dynamicSmemBytes = P3_SMEM;
+            cfg.stream = (cudaStream_t)stream;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+            SVLN_CUDA(cudaLaunchKernelEx(&cfg, attn_prefill3_kernel<true>, map, p));
+        } else {
+            attn_prefill3_kernel<false><<<grid, P3_THREADS, P3_SMEM, (cudaStream_t)stream>>>(map, p);
+        }
         if (n_splits > 1) {
             dim3 cgrid(tiles, arena->n_kv_head);
             attn_prefill3_combine_kernel<<<cgrid, 256, 0, (cudaStream_t)stream>>>(p);
