@@ -244,6 +244,50 @@ int svln_gemv(const void* W, const void* x, const void* bias, void* out, int M, 
 int svln_argmax(const void* logits, int is_f32, int64_t n_rows, int64_t vocab,
                 int64_t* out_idx, svln_stream_t stream);
 
+/* ----------------------------------------------------------------------------------------
+ * Fused decode stack: one persistent launch = one greedy decode step of ONE stream (n_stream = 1)
+ * (embedding row -> n_layer x [RMSNorm, QKV + bias + RoPE + append to the arena, split-KV attention, O,
+ *  RMSNorm, SwiGLU MLP] -> final norm -> lm_head -> argmax).  Replaces the per-token forward of HF's greedy
+ * loop (transformers 4.45.1 GenerationMixin._sample -> Qwen2ForCausalLM.forward; reached from
+ * streamvln/model/stream_video_vln.py:340 and :402) for the action-token decode, which at batch 1 is pure
+ * weight streaming.  Same rounding points as the launch-per-op path (svln_add_rmsnorm, svln_gemv,
+ * svln_kv_append_rope, svln_attn_decode, svln_swiglu, svln_argmax).
+ *   kv_len[b] INCLUDES the token fed in this step (its position is kv_len[b] - 1; the caller bumps the
+ *   length before the call, as for svln_attn_decode).  All pointers are device pointers.
+ *   layer_ptrs: int64 [n_layer][8] = {w_qkv [ (Hq+2Hkv)*128, hidden ], b_qkv (or 0), w_o [hidden, Hq*128],
+ *   w_gate_up [2*inter, hidden] (gate rows then up rows), w_down [hidden, inter], ln1, ln2, 0} (bf16).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct svln_decode_stack {
+    int32_t n_layer, hidden, inter, n_q_head, n_kv_head, head_dim, vocab;
+    int32_t n_stream;            /* 1 (arrays below keep the [n_stream] shape for a later multi-stream variant) */
+    float rms_eps, attn_scale;
+    const void* layer_ptrs;
+    const void* embed;           /* [vocab, hidden] bf16 */
+    const void* final_norm;      /* [hidden] bf16 */
+    const void* lm_head;         /* [vocab, hidden] bf16 */
+    const void* rope_cos;        /* [>= max position + 1, 128] bf16 (HF cos/sin tables) */
+    const void* rope_sin;
+    const int64_t* tok_in;       /* [n_stream] token fed in this step */
+    int64_t* tok_out;            /* [n_stream] greedy next token */
+    float* logits;               /* [n_stream, vocab] fp32 or NULL */
+    const int32_t* seq_env;      /* [n_stream] arena stream of each row */
+    const int32_t* kv_len;       /* [n_stream] */
+    void* workspace;             /* >= svln_decode_stack_workspace_bytes(), 256-byte aligned */
+    size_t workspace_bytes;
+} svln_decode_stack;
+size_t svln_decode_stack_workspace_bytes(const svln_decode_stack* desc);
+/* SVLN_ERR_RANGE when n_stream > 1 (the caller falls back to the launch-per-op path; larger batches are GEMMs). */
+int svln_decode_stack_step(const svln_kv_arena* arena, const svln_decode_stack* desc, svln_stream_t stream);
+/* A grid barrier that times out (a bug, or a grid that could not be made co-resident) does not hang the GPU: the
+ * kernel finishes and reports token -1 for every stream.  This call (synchronous) returns 0 when the last launch on
+ * desc->workspace completed normally, else the 1-based index of the barrier that gave up (cta / count: which CTA,
+ * and the arrival count it saw); -1 on a bad descriptor. */
+int svln_decode_stack_status(const svln_decode_stack* desc, int* cta, int* count);
+/* Debug aid: with SVLN_STACK_TRACE=1 in the environment CTA 0 stamps clock64 at [layer][phase 0..5][point 0..3]
+ * (phase start, GEMV start, GEMV end, before the grid barrier); copies up to max_entries stamps of the last
+ * launch to `host` (after a device synchronise by the caller) and returns how many. */
+int svln_decode_stack_trace(long long* host, int max_entries);
+
 #ifdef __cplusplus
 }
 #endif

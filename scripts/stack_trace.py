@@ -1,0 +1,50 @@
+"""Per-phase cycle breakdown of the fused decode stack (CTA 0), 7B shapes.  SVLN_STACK_TRACE=1 is set here."""
+import os, sys
+os.environ["SVLN_STACK_TRACE"] = "1"
+from pathlib import Path
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+import ctypes as C
+import numpy as np
+import torch
+from streamvln_b200.qwen2 import Qwen2Config, Qwen2Engine, Qwen2Weights, Chunk
+
+which = sys.argv[1] if len(sys.argv) > 1 else "7b"
+n_ctx = int(sys.argv[2]) if len(sys.argv) > 2 else 3000
+dev = torch.device("cuda:0")
+cfg = Qwen2Config.tiny(vocab_size=512, layers=3) if which == "tiny" else Qwen2Config()
+w = Qwen2Weights.random(cfg, dev, seed=0)
+eng = Qwen2Engine(cfg, w, n_env=1, device=dev)
+emb = (torch.randn(n_ctx, cfg.hidden_size) * 0.05).bfloat16().to(dev)
+tok = eng.forward(emb, [Chunk(0, 0, n_ctx, n_ctx)]).argmax(-1)
+runner = eng._decode_runner([0], False)
+for _ in range(5):
+    tok = runner.step(tok)
+torch.cuda.synchronize()
+L = cfg.num_hidden_layers
+buf = np.zeros((L + 1) * 6 * 8 + 8, dtype=np.int64)
+n = eng.lib.svln_decode_stack_trace(buf.ctypes.data_as(C.c_void_p), buf.size)
+ad = buf[-8:].astype(np.float64)
+t = buf[:-8].reshape(L + 1, 6, 8).astype(np.float64)
+mid = slice(2, L - 2)
+# points: 0 phase entry (rowmap + first weight loads issued next), 1 after the grid barrier, 3 x ready (GEMV main
+# loop starts), 4 GEMV done, 5 epilogue done.  attention (phase 1): 0 start, 5 end.
+print("cycles, CTA 0, mean over layers 2..L-3")
+print("phase      issue+barrier  preamble      gemv  epilogue")
+tot = 0
+for ph, nm in ((0, "qkv"), (2, "o"), (3, "gate_up"), (4, "down")):
+    bar = (t[mid, ph, 1] - t[mid, ph, 0]).mean()
+    pre = (t[mid, ph, 3] - t[mid, ph, 1]).mean()
+    gemv = (t[mid, ph, 4] - t[mid, ph, 3]).mean()
+    epi = (t[mid, ph, 5] - t[mid, ph, 4]).mean()
+    print(f"{nm:8s} {bar:14.0f} {pre:9.0f} {gemv:9.0f} {epi:9.0f}")
+    tot += bar + pre + gemv + epi
+qkv_to_attn = (t[mid, 1, 0] - t[mid, 0, 5]).mean()
+attn = (t[mid, 1, 5] - t[mid, 1, 0]).mean()
+print(f"barrier qkv->attn {qkv_to_attn:.0f}; attention work (CTA 0) {attn:.0f}: item {(t[mid,1,1]-t[mid,1,0]).mean():.0f}, "
+      f"fence+sync {(t[mid,1,2]-t[mid,1,1]).mean():.0f}, atomic {(t[mid,1,3]-t[mid,1,2]).mean():.0f}, "
+      f"combine/rest {(t[mid,1,5]-t[mid,1,3]).mean():.0f}")
+tot += qkv_to_attn + attn
+layer = (t[3:L - 1, 0, 0] - t[2:L - 2, 0, 0]).mean()
+print(f"sum {tot:.0f}; layer period {layer:.0f} cycles; whole step {(t[L,0,5]-t[0,0,0]):.0f} cycles")
+print("attention item (last layer, CTA 0): q loads issued %.0f, first tile landed %.0f, tiles done %.0f, merge staged %.0f, partial written %.0f" %
+      tuple(ad[i] - ad[0] for i in range(1, 6)))

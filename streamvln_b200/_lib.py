@@ -39,6 +39,21 @@ class KvArenaStruct(C.Structure):
     ]
 
 
+class DecodeStackStruct(C.Structure):
+    """Mirror of `struct svln_decode_stack`."""
+
+    _fields_ = [
+        ("n_layer", C.c_int32), ("hidden", C.c_int32), ("inter", C.c_int32), ("n_q_head", C.c_int32),
+        ("n_kv_head", C.c_int32), ("head_dim", C.c_int32), ("vocab", C.c_int32), ("n_stream", C.c_int32),
+        ("rms_eps", C.c_float), ("attn_scale", C.c_float),
+        ("layer_ptrs", C.c_void_p), ("embed", C.c_void_p), ("final_norm", C.c_void_p), ("lm_head", C.c_void_p),
+        ("rope_cos", C.c_void_p), ("rope_sin", C.c_void_p),
+        ("tok_in", C.c_void_p), ("tok_out", C.c_void_p), ("logits", C.c_void_p),
+        ("seq_env", C.c_void_p), ("kv_len", C.c_void_p),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+    ]
+
+
 _vp, _i, _i64, _f, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_size_t
 _arena_p = C.POINTER(KvArenaStruct)
 
@@ -76,6 +91,10 @@ PROTOTYPES = {
     "svln_swiglu": (_i, [_vp, _i64, _i, _vp, _vp]),
     "svln_gemv": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "svln_argmax": (_i, [_vp, _i, _i64, _i64, _vp, _vp]),
+    "svln_decode_stack_workspace_bytes": (C.c_size_t, [C.POINTER(DecodeStackStruct)]),
+    "svln_decode_stack_status": (_i, [C.POINTER(DecodeStackStruct), _vp, _vp]),
+    "svln_decode_stack_trace": (_i, [_vp, _i]),
+    "svln_decode_stack_step": (_i, [C.POINTER(KvArenaStruct), C.POINTER(DecodeStackStruct), _vp]),
 }
 
 _lib = None

@@ -1,0 +1,879 @@
+// Fused decode stack: ONE persistent kernel runs a whole greedy decode step (embedding row -> every Qwen2
+// layer -> final norm -> lm_head -> argmax) for one or two streams.
+//
+// What it replaces: HF's per-token forward inside GenerationMixin's greedy loop (transformers 4.45.1; reached
+// from StreamVLNForCausalLM.generate, stream_video_vln.py:340 / :402).  At batch 1 that step is nothing but
+// streaming the 15.2 GB of bf16 weights once per token, and the
+// launch-per-op form (10 kernels per layer, cuBLAS GEMV + small fused ops, even inside a CUDA graph) spends a
+// third of its time in kernel boundaries: every one of the ~290 launches drains and refills the HBM pipe.
+//
+// Design (B200: 148 SMs, ~6.5 TB/s measured HBM copy peak, 126 MB L2):
+//   * grid = one CTA per SM (cooperative launch), 8 warps; phases separated by a grid barrier (one L2 atomic
+//     + spin per CTA).  5 barriers per layer: QKV | attention | O | gate/up | down.
+//   * every linear is a weight-streaming GEMV on the legacy tensor path: W rows are the 16-row A operand of
+//     mma.m16n8k16 and the (<= 2) activation vectors are columns of the B operand.  The k index inside an MMA is
+//     a free permutation as long as A and B agree, so a lane loads 16 contiguous bytes of a W row straight from
+//     global memory into its A fragment (no shared-memory staging, no unpack/FMA work) and the matching 16
+//     bytes of x from shared memory.  Warps interleave over k (step S -> warp S % 8), so a CTA sweeps its 16
+//     rows front to back; 8 iterations (16 x 16 B per lane, 64 KB per SM) are kept in flight as cp.async groups
+//     into lane-private shared-memory slots (a register ring is serialised by the per-warp scoreboards).
+//   * rows are dealt to CTAs through a per-phase row map: QKV rows come in RoPE pairs (d, d+64) so the epilogue
+//     applies bias + RoPE and writes Q / the new K,V rows of the arena directly; gate and up rows come in pairs
+//     so the epilogue applies SwiGLU; the residual adds and RMSNorms are recomputed by every CTA in the preamble
+//     of the phase that needs them (7 KB from L2) instead of being a phase of their own.
+//   * the first 8 steps of a phase's weights are issued BEFORE the CTA waits for the previous phase and builds its
+//     x vector (they depend on nothing), so HBM latency overlaps the barrier and the preamble.  (A bulk L2
+//     prefetch of the next phase's rows - cp.async.bulk.prefetch.L2 - was measured and removed: no gain, and the
+//     prefetch instructions themselves stalled the issuing CTAs.)
+//   * attention is the split-KV work item of attn_decode.cu (attn_decode_body.cuh) run by warps 0-3; the CTA
+//     that completes the last split of a (stream, kv head) merges the partials (fixed order: deterministic).
+// Rounding points are those of the unfused path (fused_ops.cu, kv_window.cu rope8, gemv.cu), i.e. HF's bf16
+// modules; accumulation order differs from cuBLAS, which the parity tolerance (1e-2 on logits) covers.
+#include <stdlib.h>
+
+#include "attn_decode_body.cuh"
+
+namespace svln {
+
+constexpr int MK_WARPS = 8;
+constexpr int MK_THREADS = MK_WARPS * 32;
+constexpr int MK_PIPE = 8;           // k32-steps in flight per warp (64 KB per SM; 20 was measured 30 % slower)
+constexpr int MK_CAP = 304;          // rows per group (multiple of 16; gate/up pairs of one CTA at 7B: 2 x 128)
+constexpr int MK_MAX_B = 1;           // the NB = 2 instantiation faults on 7B shapes (unresolved): kept out of the ABI
+constexpr int MK_MAX_SPLITS = 32;
+constexpr int MK_XPAD = 32;          // elements between the x rows of two streams: 64 B, spreads the banks
+constexpr int MK_MISC = 4096;        // bytes of misc shared memory (reductions, flags, combine weights)
+constexpr unsigned MK_SPIN_LIMIT = 1u << 22;
+
+struct StackParams {
+    svln_kv_arena arena;
+    int n_layer, D, I, Hq, Hkv, V, G;
+    float eps, scale_log2;
+    const long long* layer_ptrs;  // [n_layer][8]: wqkv, bqkv, wo, wgu, wd, ln1, ln2, unused
+    const __nv_bfloat16 *embed, *final_norm, *lm_head, *cos_t, *sin_t;
+    const int64_t* tok_in;
+    int64_t* tok_out;
+    float* logits;                // [B][V] or nullptr
+    const int32_t *seq_env, *kv_len;
+    __nv_bfloat16 *hbuf, *qrot, *attn_out, *o, *act, *pending;
+    float *part_o, *part_m, *part_l, *best_v;
+    int* best_i;
+    unsigned* sync;               // [0] grid barrier, [16 + b*Hkv + kvh] split arrival counters (zeroed per launch)
+    int n_splits;
+    int xs_stride;                // elements between the x rows of two streams in shared memory
+    int off_part, off_rowmap, off_ring, off_misc;
+    int l2_prefetch;              // bytes of the phase's weights each CTA asks L2 for before it waits (0 = off)
+    int dbg;                      // SVLN_STACK_DBG (debug) bit 0: skip preambles, 1: skip GEMV main loop, 2: skip epilogues
+    int stop_after;               // SVLN_STACK_STOP (debug): return after this many phases, 0 = run everything
+    long long* trace;             // SVLN_STACK_TRACE: clock64 stamps of CTA 0 [layer][phase 0..5][point 0..7], else nullptr
+};
+
+#define MK_TRACE(li, ph, pt)                                                                      \
+    do {                                                                                          \
+        if (p.trace && blockIdx.x == 0 && threadIdx.x == 0) p.trace[((li) * 6 + (ph)) * 8 + (pt)] = clock64(); \
+    } while (0)
+
+__device__ __forceinline__ uint64_t make_evict_first_policy() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+// weight stream: read-only path, no L1 allocation, first to leave L2 (every byte is used once per step)
+__device__ __forceinline__ int4 ld_weight(const int4* p, uint64_t pol) {
+    int4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.s32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p), "l"(pol));
+    return r;
+}
+__device__ __forceinline__ int4 lds128u(uint32_t addr) {
+    int4 r;
+    asm volatile("ld.shared.v4.s32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
+    return r;
+}
+// 16-byte async copy global -> shared through L2 only; src_bytes = 0 zero-fills the destination
+__device__ __forceinline__ void cp_async16_hint(uint32_t dst, const void* src, int src_bytes, uint64_t pol) {
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2, %3;"
+                 ::"r"(dst), "l"(src), "r"(src_bytes), "l"(pol) : "memory");
+}
+__device__ __forceinline__ float ld_cg_f32(const float* p) {
+    float r;
+    asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(r) : "l"(p));
+    return r;
+}
+
+// All CTAs of the (co-resident) grid meet here.  `epoch` counts arrivals expected so far; the counter is zeroed
+// by a memset node before every launch.  A CTA that waits absurdly long (a bug, or a grid that is not co-resident)
+// raises the abort flag sync[1] = 1 + barrier index instead of hanging the GPU: every later wait falls through, the
+// kernel ends with garbage, and CTA 0 reports token -1 so the caller fails loudly (sync[2], sync[3] = CTA, count seen).
+__device__ __forceinline__ void grid_barrier(unsigned* sync, unsigned& epoch, int G) {
+    __syncthreads();
+    epoch += (unsigned)G;
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(sync, 1u);
+        unsigned spins = 0;
+        for (;;) {
+            unsigned v;
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(sync) : "memory");
+            if (v >= epoch) break;
+            if ((++spins & 1023u) == 0) {
+                unsigned ab;
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(ab) : "l"(sync + 1) : "memory");
+                if (ab != 0) break;
+                if (spins > MK_SPIN_LIMIT) {
+                    if (atomicCAS(sync + 1, 0u, epoch / (unsigned)G) == 0u) { sync[2] = blockIdx.x; sync[3] = v; }
+                    break;
+                }
+            }
+        }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+// ---- weight-streaming GEMV core -------------------------------------------------------------------------------
+// Partial sums of rows rowmap[0..nrows) of W (row-major [*, K]) against the NB vectors in xs.  Rows are taken in
+// nblk = ceil(nrows / 16) balanced blocks (the 16 A rows of an MMA); warp w covers k32-steps S = w, w + 8, ...;
+// partials go to part[(w * MK_CAP + r) * NB + n].
+// The W fragments travel global -> shared with cp.async into slots private to each lane (a register ring is
+// serialised by the six per-warp scoreboards: a wait on the oldest load also waits for the newest one sharing its
+// scoreboard; measured 1.3 TB/s).  cp.async groups give a true rolling pipeline of MK_PIPE steps, and no barrier is
+// needed because every lane reads back only what it copied itself.  gemv_start issues the first MK_PIPE steps -
+// it needs nothing but the weights, so the caller runs it BEFORE waiting for the previous phase (grid barrier) and
+// building x; gemv_finish streams the rest.
+struct GemvCursor {
+    int it, st, blk;            // next step to issue: flat index, step within block, block
+    const int4 *p0, *p1;        // row pointers (lane's 16 B of step 0) of rows g and g + 8 of block `blk`, or null
+};
+struct GemvGeom {
+    const int4* Wv;
+    const int* rowmap;
+    int K8, nrows, nblk, nst, total, g;
+    uint32_t slot0;
+};
+constexpr int MK_STEP = MK_WARPS * 4;              // int4 between two consecutive steps of one warp
+constexpr uint32_t MK_SLOT = MK_THREADS * 16;      // bytes between two ring slots of one lane
+
+__device__ __forceinline__ GemvGeom gemv_geom(const __nv_bfloat16* W, int K, const int* rowmap, int nrows,
+                                              unsigned char* ring) {
+    GemvGeom G;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nsteps = K >> 5;
+    G.g = lane >> 2;
+    G.nst = (nsteps - warp + MK_WARPS - 1) / MK_WARPS;
+    G.nrows = nrows;
+    G.nblk = (nrows + 15) >> 4;
+    G.total = G.nblk * G.nst;
+    G.K8 = K >> 3;
+    G.Wv = reinterpret_cast<const int4*>(W) + warp * 4 + (lane & 3);
+    G.rowmap = rowmap;
+    G.slot0 = smem_u32(ring) + threadIdx.x * 16;
+    return G;
+}
+__device__ __forceinline__ void gemv_set_block(GemvCursor& c, const GemvGeom& G) {
+    const int start = (c.blk * G.nrows) / G.nblk, size = ((c.blk + 1) * G.nrows) / G.nblk - start;
+    c.p0 = G.g < size ? G.Wv + (int64_t)G.rowmap[start + G.g] * G.K8 : nullptr;
+    c.p1 = G.g + 8 < size ? G.Wv + (int64_t)G.rowmap[start + G.g + 8] * G.K8 : nullptr;
+}
+__device__ __forceinline__ void gemv_issue(GemvCursor& c, const GemvGeom& G, int q, uint64_t pol) {
+    if (c.it < G.total) {
+        cp_async16_hint(G.slot0 + (2 * q) * MK_SLOT, c.p0 ? (const void*)(c.p0 + c.st * MK_STEP) : (const void*)G.Wv,
+                        c.p0 ? 16 : 0, pol);
+        cp_async16_hint(G.slot0 + (2 * q + 1) * MK_SLOT, c.p1 ? (const void*)(c.p1 + c.st * MK_STEP) : (const void*)G.Wv,
+                        c.p1 ? 16 : 0, pol);
+        ++c.it;
+        if (++c.st == G.nst) {
+            c.st = 0;
+            if (++c.blk < G.nblk) gemv_set_block(c, G);
+        }
+    }
+    cp_async_commit();   // always: keeps the group count in step with q
+}
+
+__device__ __noinline__ GemvCursor gemv_start(const __nv_bfloat16* __restrict__ W, int K, const int* rowmap, int nrows,
+                                              unsigned char* ring, uint64_t pol) {
+    const GemvGeom G = gemv_geom(W, K, rowmap, nrows, ring);
+    GemvCursor c;
+    c.it = c.st = c.blk = 0;
+    c.p0 = c.p1 = nullptr;
+    if (G.total > 0) gemv_set_block(c, G);
+#pragma unroll
+    for (int q = 0; q < MK_PIPE; ++q) gemv_issue(c, G, q, pol);
+    return c;
+}
+
+template <int NB>
+__device__ __noinline__ void gemv_finish(GemvCursor c, const __nv_bfloat16* __restrict__ W, int K, const int* rowmap,
+                                         int nrows, const __nv_bfloat16* xs, int xs_stride, float* part,
+                                         unsigned char* ring, uint64_t pol) {
+    const GemvGeom G = gemv_geom(W, K, rowmap, nrows, ring);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const uint32_t xv = smem_u32(xs + (g < NB ? g : 0) * xs_stride) + (warp * 4 + t) * 16;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    int c_st = 0, c_blk = 0;
+    for (int it = 0; it < G.total; it += MK_PIPE) {
+#pragma unroll
+        for (int q = 0; q < MK_PIPE; ++q) {
+            cp_async_wait<MK_PIPE - 1>();
+            if (it + q < G.total) {
+                const int4 w0 = lds128u(G.slot0 + (2 * q) * MK_SLOT);
+                const int4 w1 = lds128u(G.slot0 + (2 * q + 1) * MK_SLOT);
+                const int4 x = lds128u(xv + c_st * (MK_STEP * 16));
+                const uint32_t a0[4] = {(uint32_t)w0.x, (uint32_t)w1.x, (uint32_t)w0.y, (uint32_t)w1.y};
+                const uint32_t a1[4] = {(uint32_t)w0.z, (uint32_t)w1.z, (uint32_t)w0.w, (uint32_t)w1.w};
+                mma_bf16(acc, a0, (uint32_t)x.x, (uint32_t)x.y);
+                mma_bf16(acc, a1, (uint32_t)x.z, (uint32_t)x.w);
+                if (++c_st == G.nst) {
+                    const int start = (c_blk * nrows) / G.nblk, size = ((c_blk + 1) * nrows) / G.nblk - start;
+                    float* dst = part + ((int64_t)warp * MK_CAP + start + g) * NB;
+                    if (g < size) {
+                        if (2 * t < NB) dst[2 * t] = acc[0];
+                        if (2 * t + 1 < NB) dst[2 * t + 1] = acc[1];
+                    }
+                    if (g + 8 < size) {
+                        if (2 * t < NB) dst[8 * NB + 2 * t] = acc[2];
+                        if (2 * t + 1 < NB) dst[8 * NB + 2 * t + 1] = acc[3];
+                    }
+                    acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
+                    c_st = 0;
+                    ++c_blk;
+                }
+            }
+            gemv_issue(c, G, q, pol);
+        }
+    }
+    cp_async_wait<0>();
+}
+
+// Opt-in experiment (SVLN_STACK_L2PF=bytes, default off): ask L2 for the first `budget` bytes this CTA will stream in
+// the phase with per-line prefetches before it waits in the grid barrier.  Measured on B200: the GEMV main loops do
+// not get faster (they are bound by per-warp issue latency, not by HBM latency) and the barrier gets slower; the
+// bulk form (cp.async.bulk.prefetch.L2) stalled the issuing threads outright.
+__device__ __forceinline__ void l2_prefetch_rows(const __nv_bfloat16* W, int K, const int* rowmap, int nrows, int budget) {
+    const int lpr = (K * 2) >> 7;                 // 128-byte lines per row
+    if (lpr <= 0 || budget <= 0) return;
+    const int nblk = (nrows + 15) >> 4;
+    int n = nblk * 16 * lpr;
+    if (n > (budget >> 7)) n = budget >> 7;
+    for (int idx = threadIdx.x; idx < n; idx += MK_THREADS) {
+        const int blk = idx / (16 * lpr), rem = idx - blk * 16 * lpr;
+        const int r = blk * 16 + (rem & 15), line = rem >> 4;
+        if (r < nrows) {
+            const __nv_bfloat16* a = W + (int64_t)rowmap[r] * K + line * 64;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+        }
+    }
+}
+
+// One GEMV phase of this CTA: `n_units` units of RPU rows each (row = rowfn(unit, which)); epi(unit, n, sums[RPU])
+// consumes the finished dot products.  `mid` runs exactly once, after the first weights are in flight and before
+// they are consumed: it waits for the previous phase (grid barrier) and builds x in shared memory.
+template <int NB, int RPU, class RowFn, class MidFn, class EpiFn>
+__device__ __forceinline__ void gemv_phase(const StackParams& p, unsigned char* smem, const __nv_bfloat16* W, int K,
+                                           int n_units, RowFn rowfn, MidFn mid, EpiFn epi, uint64_t pol,
+                                           int tr_li, int tr_ph) {
+    const __nv_bfloat16* xs = reinterpret_cast<const __nv_bfloat16*>(smem);
+    float* part = reinterpret_cast<float*>(smem + p.off_part);
+    int* rowmap = reinterpret_cast<int*>(smem + p.off_rowmap);
+    unsigned char* ring = smem + p.off_ring;
+    constexpr int UPG = MK_CAP / RPU;
+    const int n_active = min(MK_WARPS, K >> 5);
+    const int tid = threadIdx.x;
+    MK_TRACE(tr_li, tr_ph, 0);
+    if (n_units <= 0) { mid(); return; }
+    for (int u0 = 0; u0 < n_units; u0 += UPG) {
+        const int nu = min(UPG, n_units - u0);
+        for (int j = tid; j < nu * RPU; j += MK_THREADS) rowmap[j] = rowfn(u0 + j / RPU, j % RPU);
+        __syncthreads();
+        const GemvCursor cur = gemv_start(W, K, rowmap, nu * RPU, ring, pol);
+        if (u0 == 0) {
+            l2_prefetch_rows(W, K, rowmap, nu * RPU, p.l2_prefetch);
+            mid();
+        }
+        MK_TRACE(tr_li, tr_ph, 3);
+        if (!(p.dbg & 2)) gemv_finish<NB>(cur, W, K, rowmap, nu * RPU, xs, p.xs_stride, part, ring, pol);
+        else cp_async_wait<0>();
+        __syncthreads();
+        MK_TRACE(tr_li, tr_ph, 4);
+        for (int i = tid; i < nu * NB && !(p.dbg & 4); i += MK_THREADS) {
+            const int j = i / NB, n = i % NB;
+            float s[RPU];
+#pragma unroll
+            for (int q = 0; q < RPU; ++q) {
+                float a = 0.f;
+                for (int w = 0; w < n_active; ++w) a += part[((int64_t)w * MK_CAP + j * RPU + q) * NB + n];
+                s[q] = a;
+            }
+            epi(u0 + j, n, s);
+        }
+        __syncthreads();
+    }
+    MK_TRACE(tr_li, tr_ph, 5);
+}
+
+// x = RMSNorm(src (+ add)) * w for every stream into shared memory; CTA 0 also stores the summed residual stream.
+// src_embed: rows are looked up in the embedding table by token id (layer 0), else src is [NB][D].
+template <int NB>
+__device__ __forceinline__ void preamble_norm(const StackParams& p, unsigned char* smem, const __nv_bfloat16* src,
+                                           bool src_embed, const __nv_bfloat16* add, const __nv_bfloat16* lnw,
+                                           __nv_bfloat16* h_out) {
+    __nv_bfloat16* xs = reinterpret_cast<__nv_bfloat16*>(smem);
+    float* red = reinterpret_cast<float*>(smem + p.off_misc);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int D8 = p.D >> 3;
+    constexpr int MAXQ = 2;  // D <= 256 * 2 * 8 = 4096
+    int4 v[NB][MAXQ], a[NB][MAXQ], wv[MAXQ];
+    // every load first (one L2 round trip), arithmetic after
+#pragma unroll
+    for (int n = 0; n < NB; ++n) {
+        const int4* s;
+        if (src_embed) {
+            int64_t tok = p.tok_in[n];
+            tok = tok < 0 ? 0 : (tok >= p.V ? p.V - 1 : tok);
+            s = reinterpret_cast<const int4*>(p.embed + tok * p.D);
+        } else {
+            s = reinterpret_cast<const int4*>(src + (int64_t)n * p.D);
+        }
+#pragma unroll
+        for (int q = 0; q < MAXQ; ++q) {
+            const int c = q * MK_THREADS + tid;
+            if (c < D8) {
+                v[n][q] = src_embed ? __ldg(s + c) : __ldcg(s + c);
+                if (add) a[n][q] = __ldcg(reinterpret_cast<const int4*>(add + (int64_t)n * p.D) + c);
+            }
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < MAXQ; ++q) {
+        const int c = q * MK_THREADS + tid;
+        if (c < D8) wv[q] = __ldg(reinterpret_cast<const int4*>(lnw) + c);
+    }
+#pragma unroll
+    for (int n = 0; n < NB; ++n) {
+        float ss = 0.f;
+#pragma unroll
+        for (int q = 0; q < MAXQ; ++q) {
+            const int c = q * MK_THREADS + tid;
+            if (c < D8) {
+                uint32_t* u = reinterpret_cast<uint32_t*>(&v[n][q]);
+                if (add) {
+                    const uint32_t* ru = reinterpret_cast<const uint32_t*>(&a[n][q]);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const float a0 = bf16_bits_to_f32(u[k] & 0xFFFFu) + bf16_bits_to_f32(ru[k] & 0xFFFFu);
+                        const float a1 = bf16_bits_to_f32(u[k] >> 16) + bf16_bits_to_f32(ru[k] >> 16);
+                        u[k] = f32_to_bf16_bits(a0) | (f32_to_bf16_bits(a1) << 16);
+                    }
+                }
+                if (h_out && blockIdx.x == 0) reinterpret_cast<int4*>(h_out + (int64_t)n * p.D)[c] = v[n][q];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float a0 = bf16_bits_to_f32(u[k] & 0xFFFFu), a1 = bf16_bits_to_f32(u[k] >> 16);
+                    ss += a0 * a0 + a1 * a1;
+                }
+            }
+        }
+        ss = warp_sum(ss);
+        if (lane == 0) red[n * MK_WARPS + warp] = ss;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int n = 0; n < NB; ++n) {
+        float tot = 0.f;
+#pragma unroll
+        for (int i = 0; i < MK_WARPS; ++i) tot += red[n * MK_WARPS + i];
+        const float rstd = rsqrtf(tot * (1.0f / (float)p.D) + p.eps);
+#pragma unroll
+        for (int q = 0; q < MAXQ; ++q) {
+            const int c = q * MK_THREADS + tid;
+            if (c < D8) {
+                const uint32_t* wu = reinterpret_cast<const uint32_t*>(&wv[q]);
+                const uint32_t* u = reinterpret_cast<const uint32_t*>(&v[n][q]);
+                int4 o;
+                uint32_t* ou = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float n0 = round_bf16(bf16_bits_to_f32(u[k] & 0xFFFFu) * rstd);
+                    const float n1 = round_bf16(bf16_bits_to_f32(u[k] >> 16) * rstd);
+                    const float y0 = bf16_bits_to_f32(wu[k] & 0xFFFFu) * n0;
+                    const float y1 = bf16_bits_to_f32(wu[k] >> 16) * n1;
+                    ou[k] = f32_to_bf16_bits(y0) | (f32_to_bf16_bits(y1) << 16);
+                }
+                reinterpret_cast<int4*>(xs + (int64_t)n * p.xs_stride)[c] = o;
+            }
+        }
+    }
+    __syncthreads();
+}
+
+// x = src[NB][K] (written earlier in this launch by other CTAs) into shared memory, 8 loads in flight per thread
+template <int NB>
+__device__ __forceinline__ void preamble_copy(const StackParams& p, unsigned char* smem, const __nv_bfloat16* src, int K) {
+    __nv_bfloat16* xs = reinterpret_cast<__nv_bfloat16*>(smem);
+    const int K8 = K >> 3, total = NB * K8;
+    const int4* s4 = reinterpret_cast<const int4*>(src);
+    for (int base = 0; base < total; base += MK_THREADS * 8) {
+        int4 tmp[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int c = base + u * MK_THREADS + threadIdx.x;
+            if (c < total) tmp[u] = __ldcg(s4 + c);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int c = base + u * MK_THREADS + threadIdx.x;
+            if (c < total) {
+                const int n = c / K8, cc = c - n * K8;
+                reinterpret_cast<int4*>(xs + (int64_t)n * p.xs_stride)[cc] = tmp[u];
+            }
+        }
+    }
+    __syncthreads();
+}
+
+// merge the split partials of (stream b, kv head kvh): warp <-> query row, lane <-> 4 dims; same arithmetic and
+// split order as attn_decode_combine_kernel, with all loads of a row in flight together
+__device__ __noinline__ void combine_splits(const StackParams& p, int b, int kvh) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = p.Hq / p.Hkv;
+    const int64_t slot0 = ((int64_t)b * p.Hkv + kvh) * p.n_splits;
+    for (int r = warp; r < g; r += MK_WARPS) {
+        const float ms = lane < p.n_splits ? __ldcg(p.part_m + (slot0 + lane) * DROWS + r) : -INFINITY;
+        const float m = warp_max(ms);
+        const float w = (lane < p.n_splits && ms != -INFINITY) ? exp2f((ms - m) * p.scale_log2) : 0.f;
+        float l = lane < p.n_splits ? __ldcg(p.part_l + (slot0 + lane) * DROWS + r) * w : 0.f;
+        l = warp_sum(l);
+        const float4* po = reinterpret_cast<const float4*>(p.part_o + (slot0 * DROWS + r) * HD) + lane;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int s0 = 0; s0 < p.n_splits; s0 += 16) {
+            float4 v[16];
+#pragma unroll
+            for (int u = 0; u < 16; ++u)
+                if (s0 + u < p.n_splits) v[u] = __ldcg(po + (int64_t)(s0 + u) * (DROWS * HD / 4));
+#pragma unroll
+            for (int u = 0; u < 16; ++u) {
+                const float ws = __shfl_sync(0xffffffffu, w, (s0 + u) & 31);
+                if (s0 + u < p.n_splits && ws != 0.f) {   // empty splits hold stale data: skipped
+                    acc.x += v[u].x * ws; acc.y += v[u].y * ws; acc.z += v[u].z * ws; acc.w += v[u].w * ws;
+                }
+            }
+        }
+        const float inv_ok = l > 0.f ? 1.f : 0.f;
+        const float o0 = inv_ok != 0.f ? acc.x / l : 0.f, o1 = inv_ok != 0.f ? acc.y / l : 0.f;
+        const float o2 = inv_ok != 0.f ? acc.z / l : 0.f, o3 = inv_ok != 0.f ? acc.w / l : 0.f;
+        uint2 packed;
+        packed.x = pack_bf16(o0, o1);
+        packed.y = pack_bf16(o2, o3);
+        *reinterpret_cast<uint2*>(p.attn_out + ((int64_t)b * p.Hq + kvh * g + r) * HD + lane * 4) = packed;
+    }
+}
+
+template <int MODE>
+__device__ __noinline__ void attn_item(const DecodeParams& dp, int split, int kvh, int b, unsigned char* smem, int tid) {
+    attn_decode_body<1, MODE>(dp, split, kvh, b, smem, tid);
+}
+
+template <int NB>
+__global__ void __launch_bounds__(MK_THREADS, 1)
+decode_stack_kernel(const __grid_constant__ StackParams p) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int c = blockIdx.x, G = p.G;
+    const int D = p.D, I = p.I, Hq = p.Hq, Hkv = p.Hkv;
+    const uint64_t pol = make_evict_first_policy();
+    unsigned epoch = 0;
+    int phases_left = p.stop_after > 0 ? p.stop_after : 0x7FFFFFFF;
+#define MK_PHASE_DONE() do { if (--phases_left == 0) return; } while (0)
+    int* s_misc_i = reinterpret_cast<int*>(smem + p.off_misc);   // floats 0..31: norm partials; ints 32..47: flags
+    int* s_flag = s_misc_i + 32;
+    int* s_qstart = s_misc_i + 36;  // [NB]
+    int* s_nq = s_misc_i + 40;      // [NB]
+    if (tid < NB) { s_qstart[tid] = tid; s_nq[tid] = 1; }
+
+    // this CTA's share of each phase (balanced contiguous ranges)
+    const int n_pairs_all = (Hq + 2 * Hkv) * 64;
+    const int qkv_p0 = (int)((int64_t)n_pairs_all * c / G), qkv_p1 = (int)((int64_t)n_pairs_all * (c + 1) / G);
+    const int d_r0 = (int)((int64_t)D * c / G), d_r1 = (int)((int64_t)D * (c + 1) / G);
+    const int i_r0 = (int)((int64_t)I * c / G), i_r1 = (int)((int64_t)I * (c + 1) / G);
+    const int v_r0 = (int)((int64_t)p.V * c / G), v_r1 = (int)((int64_t)p.V * (c + 1) / G);
+    auto qkv_row = [&](int u, int which) { const int pr = qkv_p0 + u; return (pr >> 6) * 128 + (pr & 63) + which * 64; };
+    auto d_row = [&](int u, int) { return d_r0 + u; };
+    auto gu_row = [&](int u, int which) { return i_r0 + u + which * I; };
+    auto v_row = [&](int u, int) { return v_r0 + u; };
+
+    int pos[NB], env[NB];
+    int max_len = 1;
+#pragma unroll
+    for (int n = 0; n < NB; ++n) {
+        const int len = p.kv_len[n];
+        pos[n] = len - 1;
+        env[n] = p.seq_env[n];
+        max_len = max(max_len, len);
+    }
+    DecodeParams dp;
+    dp.arena = p.arena;
+    dp.q = p.qrot;
+    dp.n_q_head = Hq;
+    dp.seq_env = p.seq_env;
+    dp.q_start = s_qstart;
+    dp.n_q = s_nq;
+    dp.kv_len = p.kv_len;
+    dp.groups_per_seq = 1;
+    dp.tok_per_group = DROWS / (Hq / Hkv);
+    dp.n_splits = p.n_splits;
+    dp.split_keys = (((max_len + p.n_splits - 1) / p.n_splits + DT - 1) / DT) * DT;
+    dp.scale_log2 = p.scale_log2;
+    dp.part_o = p.part_o;
+    dp.part_m = p.part_m;
+    dp.part_l = p.part_l;
+    dp.out = p.attn_out;
+    dp.trace = p.trace ? p.trace + (int64_t)(p.n_layer + 1) * 6 * 8 : nullptr;   // 8 stamps of the last layer's item
+    const int n_items = NB * Hkv * p.n_splits;
+    __nv_bfloat16* hb0 = p.hbuf;
+    __nv_bfloat16* hb1 = p.hbuf + (int64_t)NB * D;
+    const int64_t plane_sz = (int64_t)p.arena.max_len * HD;
+    __nv_bfloat16* arena_base = reinterpret_cast<__nv_bfloat16*>(p.arena.base);
+
+    for (int li = 0; li < p.n_layer; ++li) {
+        const long long* L = p.layer_ptrs + (int64_t)li * 8;
+        const __nv_bfloat16* wqkv = reinterpret_cast<const __nv_bfloat16*>(__ldg(L + 0));
+        const __nv_bfloat16* bqkv = reinterpret_cast<const __nv_bfloat16*>(__ldg(L + 1));
+        const __nv_bfloat16* wo = reinterpret_cast<const __nv_bfloat16*>(__ldg(L + 2));
+        const __nv_bfloat16* wgu = reinterpret_cast<const __nv_bfloat16*>(__ldg(L + 3));
+        const __nv_bfloat16* wd = reinterpret_cast<const __nv_bfloat16*>(__ldg(L + 4));
+        const __nv_bfloat16* ln1 = reinterpret_cast<const __nv_bfloat16*>(__ldg(L + 5));
+        const __nv_bfloat16* ln2 = reinterpret_cast<const __nv_bfloat16*>(__ldg(L + 6));
+
+        // ---- QKV: hn = h (+ pending MLP output); x = RMSNorm(hn); q,k,v = x W^T + b; RoPE; append
+        gemv_phase<NB, 2>(p, smem, wqkv, D, qkv_p1 - qkv_p0, qkv_row,
+            [&] {
+                if (li > 0) grid_barrier(p.sync, epoch, G);     // previous layer's down projection
+                MK_TRACE(li, 0, 1);
+                if (!(p.dbg & 1)) preamble_norm<NB>(p, smem, hb0, li == 0, li == 0 ? nullptr : p.pending, ln1, hb1);
+            },
+            [&](int u, int n, const float (&s)[2]) {
+                const int pr = qkv_p0 + u, h = pr >> 6, d = pr & 63;
+                const int row = h * 128 + d;
+                const float xl = round_bf16(s[0] + (bqkv ? __bfloat162float(bqkv[row]) : 0.f));
+                const float xh = round_bf16(s[1] + (bqkv ? __bfloat162float(bqkv[row + 64]) : 0.f));
+                __nv_bfloat16 lo, hi;
+                if (h < Hq + Hkv) {
+                    const __nv_bfloat16* cr = p.cos_t + (int64_t)pos[n] * HD;
+                    const __nv_bfloat16* sr = p.sin_t + (int64_t)pos[n] * HD;
+                    const float a = round_bf16(__fmul_rn(xl, __bfloat162float(cr[d])));
+                    const float b = round_bf16(__fmul_rn(-xh, __bfloat162float(sr[d])));
+                    const float cc = round_bf16(__fmul_rn(xh, __bfloat162float(cr[d + 64])));
+                    const float dd = round_bf16(__fmul_rn(xl, __bfloat162float(sr[d + 64])));
+                    lo = __float2bfloat16_rn(__fadd_rn(a, b));
+                    hi = __float2bfloat16_rn(__fadd_rn(cc, dd));
+                } else {
+                    lo = __float2bfloat16_rn(xl);
+                    hi = __float2bfloat16_rn(xh);
+                }
+                __nv_bfloat16* dst;
+                if (h < Hq) {
+                    dst = p.qrot + ((int64_t)n * Hq + h) * HD;
+                } else {
+                    const int kv = h < Hq + Hkv ? 0 : 1;
+                    const int head = h - Hq - kv * Hkv;
+                    dst = arena_base + ((((int64_t)env[n] * p.arena.n_layer + li) * 2 + kv) * Hkv + head) * plane_sz +
+                          (int64_t)pos[n] * HD;
+                }
+                dst[d] = lo;
+                dst[d + 64] = hi;
+            },
+            pol, li, 0);
+        MK_PHASE_DONE();
+
+        // ---- attention: split-KV work items on warps 0-3; the CTA that completes the last split of a
+        //      (stream, kv head) merges the partials.  The first item's K/V tiles are requested before the barrier
+        //      (they predate this step except for the newest row, which is fetched again afterwards).
+        dp.layer = li;
+        if (c < n_items && warp < DWARPS)
+            attn_item<1>(dp, c % p.n_splits, (c / p.n_splits) % Hkv, c / (p.n_splits * Hkv), smem, tid);
+        grid_barrier(p.sync, epoch, G);
+        MK_TRACE(li, 1, 0);
+        for (int item = c; item < n_items; item += G) {
+            const int split = item % p.n_splits, kvh = (item / p.n_splits) % Hkv, b = item / (p.n_splits * Hkv);
+            if (warp < DWARPS) {
+                if (item == c) attn_item<2>(dp, split, kvh, b, smem, tid);
+                else attn_item<0>(dp, split, kvh, b, smem, tid);
+                MK_TRACE(li, 1, 1);
+                __threadfence();
+            }
+            __syncthreads();
+            MK_TRACE(li, 1, 2);
+            if (tid == 0) {
+                const unsigned old = atomicAdd(p.sync + 16 + b * Hkv + kvh, 1u);
+                *s_flag = ((old + 1) % (unsigned)p.n_splits) == 0;
+            }
+            __syncthreads();
+            MK_TRACE(li, 1, 3);
+            if (*s_flag) {
+                __threadfence();
+                combine_splits(p, b, kvh);
+            }
+            __syncthreads();
+        }
+        MK_TRACE(li, 1, 5);
+        MK_PHASE_DONE();
+
+        // ---- O projection
+        gemv_phase<NB, 1>(p, smem, wo, Hq * HD, d_r1 - d_r0, d_row,
+            [&] {
+                grid_barrier(p.sync, epoch, G);
+                MK_TRACE(li, 2, 1);
+                preamble_copy<NB>(p, smem, p.attn_out, Hq * HD);
+            },
+            [&](int u, int n, const float (&s)[1]) { p.o[(int64_t)n * D + d_r0 + u] = __float2bfloat16_rn(s[0]); },
+            pol, li, 2);
+        MK_PHASE_DONE();
+
+        // ---- gate/up: h2 = hn + o; x = RMSNorm(h2); act = silu(x Wg^T) * (x Wu^T)
+        gemv_phase<NB, 2>(p, smem, wgu, D, i_r1 - i_r0, gu_row,
+            [&] {
+                grid_barrier(p.sync, epoch, G);
+                MK_TRACE(li, 3, 1);
+                preamble_norm<NB>(p, smem, hb1, false, p.o, ln2, hb0);
+            },
+            [&](int u, int n, const float (&s)[2]) {
+                const float gv = round_bf16(s[0]), uv = round_bf16(s[1]);
+                const float a = round_bf16(gv / (1.0f + expf(-gv)));
+                p.act[(int64_t)n * I + i_r0 + u] = __float2bfloat16_rn(a * uv);
+            },
+            pol, li, 3);
+        MK_PHASE_DONE();
+
+        // ---- down projection -> pending (added to the residual stream by the next norm)
+        gemv_phase<NB, 1>(p, smem, wd, I, d_r1 - d_r0, d_row,
+            [&] {
+                grid_barrier(p.sync, epoch, G);
+                MK_TRACE(li, 4, 1);
+                preamble_copy<NB>(p, smem, p.act, I);
+            },
+            [&](int u, int n, const float (&s)[1]) { p.pending[(int64_t)n * D + d_r0 + u] = __float2bfloat16_rn(s[0]); },
+            pol, li, 4);
+        MK_PHASE_DONE();
+    }
+
+    // ---- final norm, lm_head, greedy argmax (ties -> lowest index, as torch.argmax on these logits)
+    float best = -INFINITY;
+    int best_i = 0x7FFFFFFF;
+    gemv_phase<NB, 1>(p, smem, p.lm_head, D, v_r1 - v_r0, v_row,
+        [&] {
+            grid_barrier(p.sync, epoch, G);
+            preamble_norm<NB>(p, smem, hb0, false, p.pending, p.final_norm, nullptr);
+        },
+        [&](int u, int n, const float (&s)[1]) {
+            const int row = v_r0 + u;
+            if (p.logits) p.logits[(int64_t)n * p.V + row] = s[0];
+            if (s[0] > best) { best = s[0]; best_i = row; }
+        },
+        pol, p.n_layer, 0);
+    {
+        // threads with tid % NB == n saw stream n only (MK_THREADS is a multiple of NB)
+        float* red_v = reinterpret_cast<float*>(smem + p.off_misc) + 64;
+        int* red_i = reinterpret_cast<int*>(red_v + MK_THREADS);
+        red_v[tid] = best;
+        red_i[tid] = best_i;
+        __syncthreads();
+        if (tid < NB) {
+            float bv = -INFINITY;
+            int bi = 0x7FFFFFFF;
+            for (int j = tid; j < MK_THREADS; j += NB) {
+                const float v = red_v[j];
+                const int i = red_i[j];
+                if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
+            }
+            p.best_v[c * NB + tid] = bv;
+            p.best_i[c * NB + tid] = bi;
+        }
+    }
+    grid_barrier(p.sync, epoch, G);
+    if (c == 0 && tid < NB) {
+        float bv = -INFINITY;
+        int bi = 0x7FFFFFFF;
+        for (int j = 0; j < G; ++j) {
+            const float v = __ldcg(p.best_v + j * NB + tid);
+            const int i = __ldcg(p.best_i + j * NB + tid);
+            if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
+        }
+        const unsigned aborted = __ldcg(p.sync + 1);
+        p.tok_out[tid] = aborted ? -1 : (bi == 0x7FFFFFFF ? 0 : bi);
+    }
+}
+
+static size_t ws_align(size_t x) { return (x + 255) & ~(size_t)255; }
+
+struct StackLayout {
+    size_t hbuf, qrot, attn_out, o, act, pending, part_o, part_m, part_l, best_v, best_i, sync, total;
+};
+
+static StackLayout stack_layout(const svln_decode_stack* d, int G, int n_splits) {
+    StackLayout l;
+    const size_t B = d->n_stream, D = d->hidden, I = d->inter, Hq = d->n_q_head, Hkv = d->n_kv_head;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { const size_t at = off; off += ws_align(bytes); return at; };
+    l.hbuf = take(2 * B * D * 2);
+    l.qrot = take(B * Hq * HD * 2);
+    l.attn_out = take(B * Hq * HD * 2);
+    l.o = take(B * D * 2);
+    l.act = take(B * I * 2);
+    l.pending = take(B * D * 2);
+    const size_t slots = B * Hkv * n_splits;
+    l.part_o = take(slots * DROWS * HD * 4);
+    l.part_m = take(slots * DROWS * 4);
+    l.part_l = take(slots * DROWS * 4);
+    l.best_v = take((size_t)G * B * 4);
+    l.best_i = take((size_t)G * B * 4);
+    l.sync = take(64 * 4);
+    l.total = off;
+    return l;
+}
+
+static int stack_grid() {
+    static const int g_env = getenv("SVLN_STACK_CTAS") ? atoi(getenv("SVLN_STACK_CTAS")) : 0;
+    const int sms = sm_count();
+    return g_env > 0 && g_env <= sms ? g_env : sms;
+}
+
+static int stack_splits(int G, int B, int Hkv) {
+    int s = G / (B * Hkv);
+    if (s < 1) s = 1;
+    if (s > MK_MAX_SPLITS) s = MK_MAX_SPLITS;
+    return s;
+}
+
+static int stack_check(const svln_kv_arena* arena, const svln_decode_stack* d, const char* who) {
+    SVLN_REQUIRE(arena && arena->base && d, SVLN_ERR_INVALID, "%s: null arena / descriptor", who);
+    SVLN_REQUIRE(arena->head_dim == HD && d->head_dim == HD, SVLN_ERR_INVALID, "%s: head_dim must be 128", who);
+    SVLN_REQUIRE(d->n_stream >= 1 && d->n_stream <= MK_MAX_B, SVLN_ERR_RANGE, "%s: n_stream %d outside [1,%d]", who,
+                 d->n_stream, MK_MAX_B);
+    SVLN_REQUIRE(d->n_layer == arena->n_layer && d->n_kv_head == arena->n_kv_head, SVLN_ERR_INVALID,
+                 "%s: descriptor does not match the arena", who);
+    SVLN_REQUIRE(d->n_q_head > 0 && d->n_kv_head > 0 && d->n_q_head % d->n_kv_head == 0 &&
+                 d->n_q_head / d->n_kv_head <= DROWS, SVLN_ERR_INVALID, "%s: bad head counts", who);
+    SVLN_REQUIRE(d->hidden > 0 && d->hidden % 32 == 0 && d->hidden <= 4096 && d->inter > 0 && d->inter % 32 == 0 &&
+                 (d->n_q_head * HD) % 32 == 0 && d->vocab > 0, SVLN_ERR_INVALID,
+                 "%s: hidden/inter must be multiples of 32 (hidden <= 4096)", who);
+    return SVLN_OK;
+}
+
+}  // namespace svln
+
+using namespace svln;
+
+extern "C" {
+
+size_t svln_decode_stack_workspace_bytes(const svln_decode_stack* d) {
+    if (!d || d->n_stream < 1 || d->n_stream > MK_MAX_B || d->n_kv_head < 1) return 0;
+    const int G = stack_grid();
+    return stack_layout(d, G, stack_splits(G, d->n_stream, d->n_kv_head)).total;
+}
+
+/* debug: abort state of the last launch on this workspace: 0 = ok, else 1-based index of the grid barrier that timed
+ * out; cta / count = who gave up and the arrival count it saw.  Synchronous (cudaMemcpy). */
+int svln_decode_stack_status(const svln_decode_stack* d, int* cta, int* count) {
+    if (!d || !d->workspace) return -1;
+    const int G = stack_grid();
+    const StackLayout l = stack_layout(d, G, stack_splits(G, d->n_stream, d->n_kv_head));
+    unsigned host[4] = {0, 0, 0, 0};
+    if (cudaMemcpy(host, (unsigned char*)d->workspace + l.sync, sizeof(host), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    if (cta) *cta = (int)host[2];
+    if (count) *count = (int)host[3];
+    return (int)host[1];
+}
+
+/* debug: copies the clock64 trace of the last launch (SVLN_STACK_TRACE=1) to host; returns entries copied */
+static long long* g_trace_dev = nullptr;
+static int g_trace_n = 0;
+int svln_decode_stack_trace(long long* host, int max_entries) {
+    if (!g_trace_dev || !host) return 0;
+    const int n = max_entries < g_trace_n ? max_entries : g_trace_n;
+    if (cudaMemcpy(host, g_trace_dev, (size_t)n * sizeof(long long), cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
+    return n;
+}
+
+int svln_decode_stack_step(const svln_kv_arena* arena, const svln_decode_stack* d, svln_stream_t stream) {
+    int rc = stack_check(arena, d, "svln_decode_stack_step");
+    if (rc) return rc;
+    SVLN_REQUIRE(d->layer_ptrs && d->embed && d->final_norm && d->lm_head && d->rope_cos && d->rope_sin && d->tok_in &&
+                 d->tok_out && d->seq_env && d->kv_len && d->workspace, SVLN_ERR_INVALID,
+                 "svln_decode_stack_step: null pointer");
+    const int G = stack_grid();
+    const int B = d->n_stream;
+    StackParams p;
+    p.arena = *arena;
+    p.n_layer = d->n_layer; p.D = d->hidden; p.I = d->inter; p.Hq = d->n_q_head; p.Hkv = d->n_kv_head; p.V = d->vocab;
+    p.G = G;
+    p.eps = d->rms_eps;
+    p.scale_log2 = d->attn_scale * 1.4426950408889634f;
+    p.layer_ptrs = (const long long*)d->layer_ptrs;
+    p.embed = (const __nv_bfloat16*)d->embed;
+    p.final_norm = (const __nv_bfloat16*)d->final_norm;
+    p.lm_head = (const __nv_bfloat16*)d->lm_head;
+    p.cos_t = (const __nv_bfloat16*)d->rope_cos;
+    p.sin_t = (const __nv_bfloat16*)d->rope_sin;
+    p.tok_in = d->tok_in; p.tok_out = d->tok_out; p.logits = d->logits;
+    p.seq_env = d->seq_env; p.kv_len = d->kv_len;
+    p.n_splits = stack_splits(G, B, p.Hkv);
+    const StackLayout l = stack_layout(d, G, p.n_splits);
+    SVLN_REQUIRE(d->workspace_bytes >= l.total, SVLN_ERR_NOMEM, "svln_decode_stack_step: workspace %zu < %zu bytes",
+                 d->workspace_bytes, l.total);
+    SVLN_REQUIRE(((uintptr_t)d->workspace & 255) == 0, SVLN_ERR_INVALID, "svln_decode_stack_step: workspace not 256-B aligned");
+    unsigned char* ws = (unsigned char*)d->workspace;
+    p.hbuf = (__nv_bfloat16*)(ws + l.hbuf); p.qrot = (__nv_bfloat16*)(ws + l.qrot);
+    p.attn_out = (__nv_bfloat16*)(ws + l.attn_out); p.o = (__nv_bfloat16*)(ws + l.o);
+    p.act = (__nv_bfloat16*)(ws + l.act); p.pending = (__nv_bfloat16*)(ws + l.pending);
+    p.part_o = (float*)(ws + l.part_o); p.part_m = (float*)(ws + l.part_m); p.part_l = (float*)(ws + l.part_l);
+    p.best_v = (float*)(ws + l.best_v); p.best_i = (int*)(ws + l.best_i); p.sync = (unsigned*)(ws + l.sync);
+    const int kmax = p.I > p.D ? (p.I > p.Hq * HD ? p.I : p.Hq * HD) : (p.D > p.Hq * HD ? p.D : p.Hq * HD);
+    p.xs_stride = kmax + MK_XPAD;
+    p.off_part = (int)align_up((size_t)B * p.xs_stride * 2, 128);
+    p.off_rowmap = p.off_part + MK_WARPS * MK_CAP * B * 4;
+    p.off_ring = (int)align_up((size_t)p.off_rowmap + MK_CAP * 4, 128);
+    size_t misc = (size_t)p.off_ring + (size_t)MK_PIPE * 2 * MK_THREADS * 16;
+    if (misc < (size_t)DEC_SMEM) misc = DEC_SMEM;
+    p.off_misc = (int)misc;
+    const size_t smem = misc + MK_MISC;
+    SVLN_REQUIRE(smem <= 227 * 1024, SVLN_ERR_RANGE, "svln_decode_stack_step: %zu bytes of shared memory needed", smem);
+    static const int stop_env = getenv("SVLN_STACK_STOP") ? atoi(getenv("SVLN_STACK_STOP")) : 0;
+    p.stop_after = stop_env;
+    static const int pf_env = getenv("SVLN_STACK_L2PF") ? atoi(getenv("SVLN_STACK_L2PF")) : 0;   // measured: no gain (the loop is not latency-bound), costs issue time
+    p.l2_prefetch = pf_env;
+    static const int dbg_env = getenv("SVLN_STACK_DBG") ? atoi(getenv("SVLN_STACK_DBG")) : 0;
+    p.dbg = dbg_env;
+    static long long* trace_buf = nullptr;
+    if (getenv("SVLN_STACK_TRACE") && !trace_buf) {
+        SVLN_CUDA(cudaMalloc(&trace_buf, ((size_t)(p.n_layer + 1) * 6 * 8 + 8) * sizeof(long long)));
+        SVLN_CUDA(cudaMemset(trace_buf, 0, ((size_t)(p.n_layer + 1) * 6 * 8 + 8) * sizeof(long long)));
+    }
+    p.trace = trace_buf;
+    g_trace_dev = trace_buf;
+    g_trace_n = (p.n_layer + 1) * 6 * 8 + 8;
+    static const int coop = getenv("SVLN_STACK_COOP") ? atoi(getenv("SVLN_STACK_COOP")) : 1;
+
+    cudaStream_t st = (cudaStream_t)stream;
+    SVLN_CUDA(cudaMemsetAsync(p.sync, 0, 64 * 4, st));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(G);
+    cfg.blockDim = dim3(MK_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;
+    attr[0].val.cooperative = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = coop ? 1 : 0;
+    static size_t smem_set = 0;
+    if (smem > smem_set) {
+        SVLN_CUDA(cudaFuncSetAttribute(decode_stack_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_set = smem;
+    }
+    SVLN_CUDA(cudaLaunchKernelEx(&cfg, decode_stack_kernel<1>, p));
+    return check_launch("decode_stack_kernel");
+}
+
+}  // extern "C"

@@ -9,6 +9,7 @@ packed into one [n_tok, hidden] batch so every GEMM serves all concurrent episod
 """
 from __future__ import annotations
 
+import ctypes as C
 import os
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Sequence
@@ -146,6 +147,11 @@ class Qwen2Engine:
         self.use_graphs = os.environ.get("SVLN_NO_GRAPH", "0") != "1"
         self.use_prefill_graph = self.use_graphs
         self.use_gemv = os.environ.get("SVLN_NO_GEMV", "0") != "1"
+        # fused decode stack (one persistent launch per decode step) for a single stream; SVLN_NO_STACK=1 falls back to
+        # the launch-per-op sequence
+        self.use_stack = os.environ.get("SVLN_NO_STACK", "0") != "1"
+        self._layer_ptrs: Optional[torch.Tensor] = None
+        self.keep_decode_logits = False
         self._pgraphs: Dict[tuple, "_PrefillGraph"] = {}
         self._pseen: Dict[tuple, int] = {}
         self._prof_flops = 0.0
@@ -331,11 +337,55 @@ class Qwen2Engine:
     def _decode_runner(self, envs: Sequence[int], use_graph: bool) -> "_DecodeRunner":
         return _DecodeRunner(self, list(envs), use_graph)
 
+    STACK_MAX_STREAMS = 1
+
+    def _stack_layer_ptrs(self) -> torch.Tensor:
+        if self._layer_ptrs is None:
+            rows = [[L["wqkv"].data_ptr(), L["bqkv"].data_ptr() if L.get("bqkv") is not None else 0, L["wo"].data_ptr(),
+                     L["wgu"].data_ptr(), L["wd"].data_ptr(), L["ln1"].data_ptr(), L["ln2"].data_ptr(), 0]
+                    for L in self.w.layers]
+            self._layer_ptrs = torch.tensor(rows, dtype=torch.int64).to(self.device)
+        return self._layer_ptrs
+
+    def _stack_desc(self, state: "_DecodeState", tok: torch.Tensor):
+        """svln_decode_stack descriptor bound to this state's device tensors (built once per state)."""
+        if state.stack is None:
+            cfg = self.cfg
+            d = _lib.DecodeStackStruct()
+            d.n_layer, d.hidden, d.inter = cfg.num_hidden_layers, cfg.hidden_size, cfg.intermediate_size
+            d.n_q_head, d.n_kv_head, d.head_dim, d.vocab = cfg.num_attention_heads, cfg.num_key_value_heads, cfg.head_dim, cfg.vocab_size
+            d.n_stream = state.seq_env.numel()
+            d.rms_eps, d.attn_scale = cfg.rms_norm_eps, self.scale
+            d.layer_ptrs = self._stack_layer_ptrs().data_ptr()
+            d.embed, d.final_norm, d.lm_head = self.w.embed.data_ptr(), self.w.final_norm.data_ptr(), self.w.lm_head.data_ptr()
+            d.rope_cos, d.rope_sin = self.arena.cos.data_ptr(), self.arena.sin.data_ptr()
+            state.stack_tok_in = torch.zeros(d.n_stream, dtype=torch.int64, device=self.device)
+            state.stack_tok_out = torch.zeros(d.n_stream, dtype=torch.int64, device=self.device)
+            # fp32 logits of the step are only materialised when a caller asks for them (tests, debugging)
+            state.stack_logits = (torch.zeros(d.n_stream, cfg.vocab_size, dtype=torch.float32, device=self.device)
+                                  if self.keep_decode_logits else None)
+            d.tok_in, d.tok_out, d.logits = state.stack_tok_in.data_ptr(), state.stack_tok_out.data_ptr(), ptr(state.stack_logits)
+            d.seq_env, d.kv_len = state.seq_env.data_ptr(), state.kv_len.data_ptr()
+            nbytes = self.lib.svln_decode_stack_workspace_bytes(C.byref(d))
+            if nbytes == 0:
+                raise _lib.SvlnError(-22, "svln_decode_stack_workspace_bytes rejected the descriptor")
+            state.stack_ws = torch.zeros(nbytes + 256, dtype=torch.uint8, device=self.device)
+            base = (state.stack_ws.data_ptr() + 255) // 256 * 256
+            d.workspace, d.workspace_bytes = base, nbytes
+            state.stack = d
+        return state.stack
+
     def decode_step(self, tok: torch.Tensor, state: "_DecodeState") -> torch.Tensor:
         """One packed decode step: every stream feeds one token.  All descriptors are device tensors, so
         this sequence of launches is CUDA-graph capturable."""
         cfg = self.cfg
         state.kv_len.add_(1)
+        if self.use_stack and tok.numel() <= self.STACK_MAX_STREAMS:
+            d = self._stack_desc(state, tok)
+            state.stack_tok_in.copy_(tok)
+            check(self.lib.svln_decode_stack_step(self.arena.ref, C.byref(d), cur_stream()))
+            self.launches += 1
+            return state.stack_tok_out.clone()
         torch.sub(state.kv_len, 1, out=state.tok_pos)
         h = self.w.embed.index_select(0, tok)
         H = cfg.num_attention_heads
@@ -359,6 +409,7 @@ class _DecodeState:
         self.kv_len = torch.tensor([eng.arena.lens[e] for e in envs], dtype=torch.int32, device=dev)
         self.tok_pos = torch.empty(B, dtype=torch.int32, device=dev)
         self.max_kv = eng.arena.max_len
+        self.stack = None  # svln_decode_stack descriptor + its buffers (built on first use)
 
 
 class _DecodeRunner:

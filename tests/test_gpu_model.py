@@ -82,6 +82,88 @@ def test_engine_prefill_and_decode_logits(tiny, cuda):
         assert eng.arena.lens[0] == c0.get_seq_length() and eng.arena.lens[1] == c1.get_seq_length()
 
 
+def test_fused_decode_stack_matches_hf(tiny, cuda):
+    """svln_decode_stack_step (one persistent launch per token) vs stock transformers, eager and CUDA-graphed:
+    fp32 logits of every step within the tolerance, tokens greedy under the oracle's logits."""
+    from transformers import DynamicCache
+    from streamvln_b200.qwen2 import Chunk
+
+    m, lm = tiny
+    eng = m.engine
+    assert eng.use_stack, "the fused decode stack must be the default single-stream decode path"
+    g = torch.Generator().manual_seed(3)
+    emb = (torch.randn(150, m.config.llm.hidden_size, generator=g) * 0.05).bfloat16()
+    eng.keep_decode_logits = True
+    eng._graphs.clear()
+    try:
+        eng.arena.reset_env(0)
+        logits = eng.forward(emb.to(cuda), [Chunk(0, 0, 150, 150)])
+        c0 = DynamicCache(config=lm.config)
+        with torch.no_grad():
+            want = lm(inputs_embeds=emb[None].float(), past_key_values=c0, use_cache=True).logits[0, -1]
+        assert _rel(logits[0].cpu(), want) <= TOL
+        tok = logits.argmax(-1)
+        for use_graph in (False, True):
+            runner = eng._decode_runner([0], use_graph)
+            state = runner.graph.state if runner.graph is not None else runner.state
+            for _ in range(4):
+                fed = tok.clone()
+                tok = runner.step(tok)
+                assert state.stack is not None, "decode did not go through svln_decode_stack_step"
+                with torch.no_grad():
+                    want = lm(input_ids=fed.cpu()[None], past_key_values=c0, use_cache=True).logits[0, -1]
+                got = state.stack_logits[0].cpu()
+                assert _rel(got, want) <= TOL
+                assert int(tok) == int(got.argmax())                       # the kernel's own argmax
+                top2 = want.topk(2).values
+                assert int(tok) == int(want.argmax()) or float(top2[0] - want[int(tok)]) <= 2e-2 * float(want.abs().max())
+            runner.finish()
+            assert eng.arena.lens[0] == c0.get_seq_length()
+    finally:
+        eng.keep_decode_logits = False
+        eng._graphs.clear()
+
+
+def test_fused_decode_stack_agrees_with_launch_per_op_path(tiny, cuda):
+    """Same state, same fed tokens: every token the unfused kernel sequence picks is greedy (up to a near-tie
+    margin: accumulation orders differ) under the fused stack's fp32 logits."""
+    from streamvln_b200.qwen2 import Chunk
+
+    m, _ = tiny
+    eng = m.engine
+    g = torch.Generator().manual_seed(4)
+    emb = (torch.randn(700, m.config.llm.hidden_size, generator=g) * 0.05).bfloat16().to(cuda)
+    try:
+        eng.use_stack = False
+        eng._graphs.clear()
+        eng.arena.reset_env(1)
+        first = eng.forward(emb.clone(), [Chunk(1, 0, 700, 700)]).argmax(-1)   # forward consumes h
+        runner = eng._decode_runner([1], True)
+        tok, ref = first, []
+        for _ in range(6):
+            tok = runner.step(tok)
+            ref.append(int(tok))
+        runner.finish()
+
+        eng.use_stack, eng.keep_decode_logits = True, True
+        eng._graphs.clear()
+        eng.arena.reset_env(1)
+        assert int(eng.forward(emb.clone(), [Chunk(1, 0, 700, 700)]).argmax(-1)) == int(first)
+        runner = eng._decode_runner([1], True)
+        fed, exact = first, 0
+        for want in ref:
+            got = runner.step(fed)
+            lg = runner.graph.state.stack_logits[0]
+            assert float(lg.max() - lg[want]) <= 2e-2 * float(lg.abs().max()), (want, int(got))
+            exact += int(got) == want
+            fed = torch.tensor([want], device=cuda)
+        runner.finish()
+        assert exact >= len(ref) - 2
+    finally:
+        eng.use_stack, eng.keep_decode_logits = True, False
+        eng._graphs.clear()
+
+
 def test_generate_matches_oracle_over_a_window_boundary(tiny, cuda):
     m, lm = tiny
     m.reset(2)
