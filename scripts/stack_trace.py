@@ -21,23 +21,26 @@ for _ in range(5):
     tok = runner.step(tok)
 torch.cuda.synchronize()
 L = cfg.num_hidden_layers
-buf = np.zeros((L + 1) * 6 * 8 + 8, dtype=np.int64)
+buf = np.zeros((L + 1) * 6 * 8 + 8 + 160 * 16, dtype=np.int64)
 n = eng.lib.svln_decode_stack_trace(buf.ctypes.data_as(C.c_void_p), buf.size)
-ad = buf[-8:].astype(np.float64)
-t = buf[:-8].reshape(L + 1, 6, 8).astype(np.float64)
+nt = (L + 1) * 6 * 8
+ad = buf[nt:nt + 8].astype(np.float64)
+gt = buf[nt + 8:].reshape(160, 16).astype(np.float64)
+t = buf[:nt].reshape(L + 1, 6, 8).astype(np.float64)
 mid = slice(2, L - 2)
 # points: 0 phase entry (rowmap + first weight loads issued next), 1 after the grid barrier, 3 x ready (GEMV main
 # loop starts), 4 GEMV done, 5 epilogue done.  attention (phase 1): 0 start, 5 end.
 print("cycles, CTA 0, mean over layers 2..L-3")
-print("phase      issue+barrier  preamble      gemv  epilogue")
+print("phase      rowmap+issue  barrier wait  preamble      gemv  epilogue")
 tot = 0
 for ph, nm in ((0, "qkv"), (2, "o"), (3, "gate_up"), (4, "down")):
-    bar = (t[mid, ph, 1] - t[mid, ph, 0]).mean()
+    iss = (t[mid, ph, 2] - t[mid, ph, 0]).mean()
+    bar = (t[mid, ph, 1] - t[mid, ph, 2]).mean()
     pre = (t[mid, ph, 3] - t[mid, ph, 1]).mean()
     gemv = (t[mid, ph, 4] - t[mid, ph, 3]).mean()
     epi = (t[mid, ph, 5] - t[mid, ph, 4]).mean()
-    print(f"{nm:8s} {bar:14.0f} {pre:9.0f} {gemv:9.0f} {epi:9.0f}")
-    tot += bar + pre + gemv + epi
+    print(f"{nm:8s} {iss:13.0f} {bar:13.0f} {pre:9.0f} {gemv:9.0f} {epi:9.0f}")
+    tot += iss + bar + pre + gemv + epi
 qkv_to_attn = (t[mid, 1, 0] - t[mid, 0, 5]).mean()
 attn = (t[mid, 1, 5] - t[mid, 1, 0]).mean()
 print(f"barrier qkv->attn {qkv_to_attn:.0f}; attention work (CTA 0) {attn:.0f}: item {(t[mid,1,1]-t[mid,1,0]).mean():.0f}, "
@@ -48,3 +51,14 @@ layer = (t[3:L - 1, 0, 0] - t[2:L - 2, 0, 0]).mean()
 print(f"sum {tot:.0f}; layer period {layer:.0f} cycles; whole step {(t[L,0,5]-t[0,0,0]):.0f} cycles")
 print("attention item (last layer, CTA 0): q loads issued %.0f, first tile landed %.0f, tiles done %.0f, merge staged %.0f, partial written %.0f" %
       tuple(ad[i] - ad[0] for i in range(1, 6)))
+
+G = int((gt[:, 0] > 0).sum())
+gt = gt[:G]
+t0 = gt[:, 0].min()
+names = {0: "qkv: barrier passed", 1: "qkv: gemv done", 2: "qkv: epilogue done", 3: "attn: barrier passed", 5: "attn: items done",
+         6: "o: barrier passed", 7: "o: gemv done", 8: "o: epilogue done", 9: "gu: barrier passed", 10: "gu: gemv done",
+         11: "gu: epilogue done", 12: "down: barrier passed", 13: "down: gemv done", 14: "down: epilogue done"}
+print(f"all {G} CTAs, layer {L // 2}, ns since the first CTA passed the layer's first barrier: min / mean / max")
+for k in sorted(names):
+    v = gt[:, k] - t0
+    print(f"  {names[k]:22s} {v.min():8.0f} {v.mean():8.0f} {v.max():8.0f}   (argmax CTA {int(v.argmax())})")

@@ -1,32 +1,34 @@
 // Fused decode stack: ONE persistent kernel runs a whole greedy decode step (embedding row -> every Qwen2
-// layer -> final norm -> lm_head -> argmax) for one or two streams.
+// layer -> final norm -> lm_head -> argmax) of one stream.
 //
 // What it replaces: HF's per-token forward inside GenerationMixin's greedy loop (transformers 4.45.1; reached
 // from StreamVLNForCausalLM.generate, stream_video_vln.py:340 / :402).  At batch 1 that step is nothing but
-// streaming the 15.2 GB of bf16 weights once per token, and the
-// launch-per-op form (10 kernels per layer, cuBLAS GEMV + small fused ops, even inside a CUDA graph) spends a
-// third of its time in kernel boundaries: every one of the ~290 launches drains and refills the HBM pipe.
+// streaming the 15.2 GB of bf16 weights once per token; the launch-per-op
+// form is 10 kernels per layer (cuBLAS GEMV + small fused ops), ~290 launches per token even inside a CUDA graph.
 //
-// Design (B200: 148 SMs, ~6.5 TB/s measured HBM copy peak, 126 MB L2):
+// Design (B200: 148 SMs, 6.5 TB/s measured HBM copy peak, 126 MB L2):
 //   * grid = one CTA per SM (cooperative launch), 8 warps; phases separated by a grid barrier (one L2 atomic
 //     + spin per CTA).  5 barriers per layer: QKV | attention | O | gate/up | down.
 //   * every linear is a weight-streaming GEMV on the legacy tensor path: W rows are the 16-row A operand of
-//     mma.m16n8k16 and the (<= 2) activation vectors are columns of the B operand.  The k index inside an MMA is
-//     a free permutation as long as A and B agree, so a lane loads 16 contiguous bytes of a W row straight from
-//     global memory into its A fragment (no shared-memory staging, no unpack/FMA work) and the matching 16
-//     bytes of x from shared memory.  Warps interleave over k (step S -> warp S % 8), so a CTA sweeps its 16
-//     rows front to back; 8 iterations (16 x 16 B per lane, 64 KB per SM) are kept in flight as cp.async groups
-//     into lane-private shared-memory slots (a register ring is serialised by the per-warp scoreboards).
+//     mma.m16n8k16 and the activation vector is a column of the B operand.  The k index inside an MMA is a free
+//     permutation as long as A and B agree, so a lane copies 16 contiguous bytes of a W row into a slot of shared
+//     memory that only it reads back (cp.async: no barrier, no unpack/FMA work) and pairs it with the matching
+//     16 bytes of x.  Warps interleave over k (step S -> warp S % 8): a CTA sweeps its rows front to back.
+//     Up to 4 row blocks advance through k together (independent MMAs), 96 KB of copies in flight per SM.
 //   * rows are dealt to CTAs through a per-phase row map: QKV rows come in RoPE pairs (d, d+64) so the epilogue
 //     applies bias + RoPE and writes Q / the new K,V rows of the arena directly; gate and up rows come in pairs
 //     so the epilogue applies SwiGLU; the residual adds and RMSNorms are recomputed by every CTA in the preamble
 //     of the phase that needs them (7 KB from L2) instead of being a phase of their own.
-//   * the first 8 steps of a phase's weights are issued BEFORE the CTA waits for the previous phase and builds its
-//     x vector (they depend on nothing), so HBM latency overlaps the barrier and the preamble.  (A bulk L2
-//     prefetch of the next phase's rows - cp.async.bulk.prefetch.L2 - was measured and removed: no gain, and the
-//     prefetch instructions themselves stalled the issuing CTAs.)
+//   * the barrier is split: a CTA ARRIVES (fence + atomic) as soon as its outputs are stored, then builds the next
+//     row map and issues the next phase's first weight copies (or the attention item's K/V tiles), and only then
+//     WAITS - so HBM latency overlaps the barrier and the preamble.
 //   * attention is the split-KV work item of attn_decode.cu (attn_decode_body.cuh) run by warps 0-3; the CTA
 //     that completes the last split of a (stream, kv head) merges the partials (fixed order: deterministic).
+// Measured dead ends, kept out of the code: a register ring of LDG.128 (the six per-warp scoreboards serialise
+// it: 1.3 TB/s); a 20-deep ring (30 % slower than 8-12 steps); bulk or per-line L2 prefetch of the next phase
+// and page-touching one phase ahead (no gain: the main loops are HBM-bound, gate/up streams at 6.9 TB/s);
+// fencing after the weight prologue (the fence waits for the copies: +3-6 us per barrier); 512-byte coalesced
+// requests instead of 8 rows x 64 B (35 % slower in DRAM).
 // Rounding points are those of the unfused path (fused_ops.cu, kv_window.cu rope8, gemv.cu), i.e. HF's bf16
 // modules; accumulation order differs from cuBLAS, which the parity tolerance (1e-2 on logits) covers.
 #include <stdlib.h>
@@ -37,7 +39,6 @@ namespace svln {
 
 constexpr int MK_WARPS = 8;
 constexpr int MK_THREADS = MK_WARPS * 32;
-constexpr int MK_PIPE = 8;           // k32-steps in flight per warp (64 KB per SM; 20 was measured 30 % slower)
 constexpr int MK_CAP = 304;          // rows per group (multiple of 16; gate/up pairs of one CTA at 7B: 2 x 128)
 constexpr int MK_MAX_B = 1;           // the NB = 2 instantiation faults on 7B shapes (unresolved): kept out of the ABI
 constexpr int MK_MAX_SPLITS = 32;
@@ -62,12 +63,22 @@ struct StackParams {
     int n_splits;
     int xs_stride;                // elements between the x rows of two streams in shared memory
     int off_part, off_rowmap, off_ring, off_misc;
-    int l2_prefetch;              // bytes of the phase's weights each CTA asks L2 for before it waits (0 = off)
     int dbg;                      // SVLN_STACK_DBG (debug) bit 0: skip preambles, 1: skip GEMV main loop, 2: skip epilogues
     int stop_after;               // SVLN_STACK_STOP (debug): return after this many phases, 0 = run everything
     long long* trace;             // SVLN_STACK_TRACE: clock64 stamps of CTA 0 [layer][phase 0..5][point 0..7], else nullptr
 };
 
+__device__ __forceinline__ unsigned long long mk_globaltimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// every CTA, middle layer only: [cta][16] nanosecond stamps (globaltimer is common to all SMs) after the trace block
+#define MK_GT(li, slot_)                                                                              \
+    do {                                                                                              \
+        if (p.trace && (li) == p.n_layer / 2 && threadIdx.x == 0)                                      \
+            p.trace[(int64_t)(p.n_layer + 1) * 6 * 8 + 8 + blockIdx.x * 16 + (slot_)] = (long long)mk_globaltimer(); \
+    } while (0)
 #define MK_TRACE(li, ph, pt)                                                                      \
     do {                                                                                          \
         if (p.trace && blockIdx.x == 0 && threadIdx.x == 0) p.trace[((li) * 6 + (ph)) * 8 + (pt)] = clock64(); \
@@ -102,16 +113,25 @@ __device__ __forceinline__ float ld_cg_f32(const float* p) {
     return r;
 }
 
-// All CTAs of the (co-resident) grid meet here.  `epoch` counts arrivals expected so far; the counter is zeroed
-// by a memset node before every launch.  A CTA that waits absurdly long (a bug, or a grid that is not co-resident)
-// raises the abort flag sync[1] = 1 + barrier index instead of hanging the GPU: every later wait falls through, the
-// kernel ends with garbage, and CTA 0 reports token -1 so the caller fails loudly (sync[2], sync[3] = CTA, count seen).
-__device__ __forceinline__ void grid_barrier(unsigned* sync, unsigned& epoch, int G) {
+// Grid barrier in two halves.  grid_arrive publishes this CTA's writes (fence + one atomic); grid_wait spins until
+// every CTA has arrived.  Work that needs nothing from the other CTAs - building the next row map, issuing the
+// next phase's first weight loads - goes BETWEEN the two, and must come AFTER grid_arrive: a __threadfence() also
+// waits for the thread's outstanding cp.async loads, so fencing after the weight prologue added 3-6 us of HBM
+// latency to every barrier (measured).  The wait side needs no fence: ld.acquire + the CTA barrier order the
+// later reads.  `epoch` counts arrivals expected so far; the counter is zeroed by a memset node before every launch.
+// A CTA that waits absurdly long (a bug, or a grid that is not co-resident) raises the abort flag sync[1] = barrier
+// index instead of hanging the GPU: every later wait falls through, the kernel ends with garbage, and CTA 0 reports
+// token -1 so the caller fails loudly (sync[2], sync[3] = CTA, count seen).
+__device__ __forceinline__ void grid_arrive(unsigned* sync, unsigned& epoch, int G) {
     __syncthreads();
     epoch += (unsigned)G;
     if (threadIdx.x == 0) {
         __threadfence();
         atomicAdd(sync, 1u);
+    }
+}
+__device__ __forceinline__ void grid_wait(unsigned* sync, unsigned epoch, int G) {
+    if (threadIdx.x == 0) {
         unsigned spins = 0;
         for (;;) {
             unsigned v;
@@ -127,7 +147,6 @@ __device__ __forceinline__ void grid_barrier(unsigned* sync, unsigned& epoch, in
                 }
             }
         }
-        __threadfence();
     }
     __syncthreads();
 }
@@ -138,23 +157,30 @@ __device__ __forceinline__ void grid_barrier(unsigned* sync, unsigned& epoch, in
 // partials go to part[(w * MK_CAP + r) * NB + n].
 // The W fragments travel global -> shared with cp.async into slots private to each lane (a register ring is
 // serialised by the six per-warp scoreboards: a wait on the oldest load also waits for the newest one sharing its
-// scoreboard; measured 1.3 TB/s).  cp.async groups give a true rolling pipeline of MK_PIPE steps, and no barrier is
-// needed because every lane reads back only what it copied itself.  gemv_start issues the first MK_PIPE steps -
-// it needs nothing but the weights, so the caller runs it BEFORE waiting for the previous phase (grid barrier) and
-// building x; gemv_finish streams the rest.
+// scoreboard; measured 1.3 TB/s).  cp.async groups give a true rolling pipeline, and no barrier is needed because
+// every lane reads back only what it copied itself.  gemv_start fills the ring - it needs nothing but the weights,
+// so the caller runs it BEFORE waiting for the previous phase (grid barrier) and building x; gemv_finish streams
+// the rest.
+constexpr int MK_RING_SLOTS = 24;                  // 4 KB ring slots (one lane-private int4 per thread each): 96 KB
+constexpr int MK_MAX_SB = 4;
 struct GemvCursor {
-    int it, st, blk;            // next step to issue: flat index, step within block, block
-    const int4 *p0, *p1;        // row pointers (lane's 16 B of step 0) of rows g and g + 8 of block `blk`, or null
+    int it, st, sup;                  // next step to issue: flat index, step within the super-block, super-block
+    const int4* p[MK_MAX_SB][2];      // row pointers (lane's 16 B of step 0) of rows g, g + 8 of each block, or null
 };
 struct GemvGeom {
     const int4* Wv;
     const int* rowmap;
-    int K8, nrows, nblk, nst, total, g;
+    int K8, nrows, nblk, nsup, nst, total, g;
     uint32_t slot0;
 };
 constexpr int MK_STEP = MK_WARPS * 4;              // int4 between two consecutive steps of one warp
 constexpr uint32_t MK_SLOT = MK_THREADS * 16;      // bytes between two ring slots of one lane
 
+// A super-block is SB consecutive row blocks (of <= 16 rows, balanced) that advance through k together: one
+// iteration = one k32-step of SB blocks = 2 SB cp.async per lane, 1 x fragment, 2 SB independent MMAs.  The ring
+// holds DEPTH = 12 / SB iterations.  (With one block per iteration the loop was bound by the per-warp dependent
+// latency - wait, LDS, two chained MMAs: ~340 cycles per KB-sized step whatever the phase - not by HBM.)
+template <int SB>
 __device__ __forceinline__ GemvGeom gemv_geom(const __nv_bfloat16* W, int K, const int* rowmap, int nrows,
                                               unsigned char* ring) {
     GemvGeom G;
@@ -164,107 +190,126 @@ __device__ __forceinline__ GemvGeom gemv_geom(const __nv_bfloat16* W, int K, con
     G.nst = (nsteps - warp + MK_WARPS - 1) / MK_WARPS;
     G.nrows = nrows;
     G.nblk = (nrows + 15) >> 4;
-    G.total = G.nblk * G.nst;
+    G.nsup = (G.nblk + SB - 1) / SB;
+    G.total = G.nsup * G.nst;
     G.K8 = K >> 3;
     G.Wv = reinterpret_cast<const int4*>(W) + warp * 4 + (lane & 3);
     G.rowmap = rowmap;
     G.slot0 = smem_u32(ring) + threadIdx.x * 16;
     return G;
 }
-__device__ __forceinline__ void gemv_set_block(GemvCursor& c, const GemvGeom& G) {
-    const int start = (c.blk * G.nrows) / G.nblk, size = ((c.blk + 1) * G.nrows) / G.nblk - start;
-    c.p0 = G.g < size ? G.Wv + (int64_t)G.rowmap[start + G.g] * G.K8 : nullptr;
-    c.p1 = G.g + 8 < size ? G.Wv + (int64_t)G.rowmap[start + G.g + 8] * G.K8 : nullptr;
+template <int SB>
+__device__ __forceinline__ void gemv_set_super(GemvCursor& c, const GemvGeom& G) {
+#pragma unroll
+    for (int j = 0; j < SB; ++j) {
+        const int blk = c.sup * SB + j;
+        c.p[j][0] = c.p[j][1] = nullptr;
+        if (blk < G.nblk) {
+            const int start = (blk * G.nrows) / G.nblk, size = ((blk + 1) * G.nrows) / G.nblk - start;
+            if (G.g < size) c.p[j][0] = G.Wv + (int64_t)G.rowmap[start + G.g] * G.K8;
+            if (G.g + 8 < size) c.p[j][1] = G.Wv + (int64_t)G.rowmap[start + G.g + 8] * G.K8;
+        }
+    }
 }
+template <int SB>
 __device__ __forceinline__ void gemv_issue(GemvCursor& c, const GemvGeom& G, int q, uint64_t pol) {
     if (c.it < G.total) {
-        cp_async16_hint(G.slot0 + (2 * q) * MK_SLOT, c.p0 ? (const void*)(c.p0 + c.st * MK_STEP) : (const void*)G.Wv,
-                        c.p0 ? 16 : 0, pol);
-        cp_async16_hint(G.slot0 + (2 * q + 1) * MK_SLOT, c.p1 ? (const void*)(c.p1 + c.st * MK_STEP) : (const void*)G.Wv,
-                        c.p1 ? 16 : 0, pol);
+        const int nsb = min(SB, G.nblk - c.sup * SB);
+#pragma unroll
+        for (int j = 0; j < SB; ++j) {
+            if (j < nsb) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int4* src = c.p[j][h];
+                    cp_async16_hint(G.slot0 + ((q * SB + j) * 2 + h) * MK_SLOT,
+                                    src ? (const void*)(src + c.st * MK_STEP) : (const void*)G.Wv, src ? 16 : 0, pol);
+                }
+            }
+        }
         ++c.it;
         if (++c.st == G.nst) {
             c.st = 0;
-            if (++c.blk < G.nblk) gemv_set_block(c, G);
+            if (++c.sup < G.nsup) gemv_set_super<SB>(c, G);
         }
     }
     cp_async_commit();   // always: keeps the group count in step with q
 }
 
+template <int SB>
 __device__ __noinline__ GemvCursor gemv_start(const __nv_bfloat16* __restrict__ W, int K, const int* rowmap, int nrows,
                                               unsigned char* ring, uint64_t pol) {
-    const GemvGeom G = gemv_geom(W, K, rowmap, nrows, ring);
+    constexpr int DEPTH = MK_RING_SLOTS / (2 * SB);
+    const GemvGeom G = gemv_geom<SB>(W, K, rowmap, nrows, ring);
     GemvCursor c;
-    c.it = c.st = c.blk = 0;
-    c.p0 = c.p1 = nullptr;
-    if (G.total > 0) gemv_set_block(c, G);
+    c.it = c.st = c.sup = 0;
 #pragma unroll
-    for (int q = 0; q < MK_PIPE; ++q) gemv_issue(c, G, q, pol);
+    for (int j = 0; j < MK_MAX_SB; ++j) c.p[j][0] = c.p[j][1] = nullptr;
+    if (G.total > 0) gemv_set_super<SB>(c, G);
+#pragma unroll
+    for (int q = 0; q < DEPTH; ++q) gemv_issue<SB>(c, G, q, pol);
     return c;
 }
 
-template <int NB>
+template <int NB, int SB>
 __device__ __noinline__ void gemv_finish(GemvCursor c, const __nv_bfloat16* __restrict__ W, int K, const int* rowmap,
                                          int nrows, const __nv_bfloat16* xs, int xs_stride, float* part,
                                          unsigned char* ring, uint64_t pol) {
-    const GemvGeom G = gemv_geom(W, K, rowmap, nrows, ring);
+    constexpr int DEPTH = MK_RING_SLOTS / (2 * SB);
+    const GemvGeom G = gemv_geom<SB>(W, K, rowmap, nrows, ring);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2, t = lane & 3;
     const uint32_t xv = smem_u32(xs + (g < NB ? g : 0) * xs_stride) + (warp * 4 + t) * 16;
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    int c_st = 0, c_blk = 0;
-    for (int it = 0; it < G.total; it += MK_PIPE) {
+    float acc[SB][2][4];
 #pragma unroll
-        for (int q = 0; q < MK_PIPE; ++q) {
-            cp_async_wait<MK_PIPE - 1>();
+    for (int j = 0; j < SB; ++j)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[j][0][e] = acc[j][1][e] = 0.f;
+    int c_st = 0, c_sup = 0;
+    for (int it = 0; it < G.total; it += DEPTH) {
+#pragma unroll
+        for (int q = 0; q < DEPTH; ++q) {
+            cp_async_wait<DEPTH - 1>();
             if (it + q < G.total) {
-                const int4 w0 = lds128u(G.slot0 + (2 * q) * MK_SLOT);
-                const int4 w1 = lds128u(G.slot0 + (2 * q + 1) * MK_SLOT);
+                const int nsb = min(SB, G.nblk - c_sup * SB);
                 const int4 x = lds128u(xv + c_st * (MK_STEP * 16));
-                const uint32_t a0[4] = {(uint32_t)w0.x, (uint32_t)w1.x, (uint32_t)w0.y, (uint32_t)w1.y};
-                const uint32_t a1[4] = {(uint32_t)w0.z, (uint32_t)w1.z, (uint32_t)w0.w, (uint32_t)w1.w};
-                mma_bf16(acc, a0, (uint32_t)x.x, (uint32_t)x.y);
-                mma_bf16(acc, a1, (uint32_t)x.z, (uint32_t)x.w);
+#pragma unroll
+                for (int j = 0; j < SB; ++j) {
+                    if (j < nsb) {
+                        const int4 w0 = lds128u(G.slot0 + ((q * SB + j) * 2) * MK_SLOT);
+                        const int4 w1 = lds128u(G.slot0 + ((q * SB + j) * 2 + 1) * MK_SLOT);
+                        const uint32_t a0[4] = {(uint32_t)w0.x, (uint32_t)w1.x, (uint32_t)w0.y, (uint32_t)w1.y};
+                        const uint32_t a1[4] = {(uint32_t)w0.z, (uint32_t)w1.z, (uint32_t)w0.w, (uint32_t)w1.w};
+                        mma_bf16(acc[j][0], a0, (uint32_t)x.x, (uint32_t)x.y);
+                        mma_bf16(acc[j][1], a1, (uint32_t)x.z, (uint32_t)x.w);
+                    }
+                }
                 if (++c_st == G.nst) {
-                    const int start = (c_blk * nrows) / G.nblk, size = ((c_blk + 1) * nrows) / G.nblk - start;
-                    float* dst = part + ((int64_t)warp * MK_CAP + start + g) * NB;
-                    if (g < size) {
-                        if (2 * t < NB) dst[2 * t] = acc[0];
-                        if (2 * t + 1 < NB) dst[2 * t + 1] = acc[1];
+#pragma unroll
+                    for (int j = 0; j < SB; ++j) {
+                        if (j < nsb) {
+                            const int blk = c_sup * SB + j;
+                            const int start = (blk * nrows) / G.nblk, size = ((blk + 1) * nrows) / G.nblk - start;
+                            float* dst = part + ((int64_t)warp * MK_CAP + start + g) * NB;
+                            if (g < size) {
+                                if (2 * t < NB) dst[2 * t] = acc[j][0][0] + acc[j][1][0];
+                                if (2 * t + 1 < NB) dst[2 * t + 1] = acc[j][0][1] + acc[j][1][1];
+                            }
+                            if (g + 8 < size) {
+                                if (2 * t < NB) dst[8 * NB + 2 * t] = acc[j][0][2] + acc[j][1][2];
+                                if (2 * t + 1 < NB) dst[8 * NB + 2 * t + 1] = acc[j][0][3] + acc[j][1][3];
+                            }
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) acc[j][0][e] = acc[j][1][e] = 0.f;
+                        }
                     }
-                    if (g + 8 < size) {
-                        if (2 * t < NB) dst[8 * NB + 2 * t] = acc[2];
-                        if (2 * t + 1 < NB) dst[8 * NB + 2 * t + 1] = acc[3];
-                    }
-                    acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
                     c_st = 0;
-                    ++c_blk;
+                    ++c_sup;
                 }
             }
-            gemv_issue(c, G, q, pol);
+            gemv_issue<SB>(c, G, q, pol);
         }
     }
     cp_async_wait<0>();
-}
-
-// Opt-in experiment (SVLN_STACK_L2PF=bytes, default off): ask L2 for the first `budget` bytes this CTA will stream in
-// the phase with per-line prefetches before it waits in the grid barrier.  Measured on B200: the GEMV main loops do
-// not get faster (they are bound by per-warp issue latency, not by HBM latency) and the barrier gets slower; the
-// bulk form (cp.async.bulk.prefetch.L2) stalled the issuing threads outright.
-__device__ __forceinline__ void l2_prefetch_rows(const __nv_bfloat16* W, int K, const int* rowmap, int nrows, int budget) {
-    const int lpr = (K * 2) >> 7;                 // 128-byte lines per row
-    if (lpr <= 0 || budget <= 0) return;
-    const int nblk = (nrows + 15) >> 4;
-    int n = nblk * 16 * lpr;
-    if (n > (budget >> 7)) n = budget >> 7;
-    for (int idx = threadIdx.x; idx < n; idx += MK_THREADS) {
-        const int blk = idx / (16 * lpr), rem = idx - blk * 16 * lpr;
-        const int r = blk * 16 + (rem & 15), line = rem >> 4;
-        if (r < nrows) {
-            const __nv_bfloat16* a = W + (int64_t)rowmap[r] * K + line * 64;
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
-        }
-    }
 }
 
 // One GEMV phase of this CTA: `n_units` units of RPU rows each (row = rowfn(unit, which)); epi(unit, n, sums[RPU])
@@ -287,16 +332,24 @@ __device__ __forceinline__ void gemv_phase(const StackParams& p, unsigned char* 
         const int nu = min(UPG, n_units - u0);
         for (int j = tid; j < nu * RPU; j += MK_THREADS) rowmap[j] = rowfn(u0 + j / RPU, j % RPU);
         __syncthreads();
-        const GemvCursor cur = gemv_start(W, K, rowmap, nu * RPU, ring, pol);
+        const int nrows = nu * RPU, nblk = (nrows + 15) >> 4;
+        const int sb = nblk >= 4 ? 4 : (nblk >= 2 ? 2 : 1);     // blocks advancing together (ILP) vs ring depth
+        GemvCursor cur;
+        if (sb == 4) cur = gemv_start<4>(W, K, rowmap, nrows, ring, pol);
+        else if (sb == 2) cur = gemv_start<2>(W, K, rowmap, nrows, ring, pol);
+        else cur = gemv_start<1>(W, K, rowmap, nrows, ring, pol);
+        MK_TRACE(tr_li, tr_ph, 2);
         if (u0 == 0) {
-            l2_prefetch_rows(W, K, rowmap, nu * RPU, p.l2_prefetch);
             mid();
         }
         MK_TRACE(tr_li, tr_ph, 3);
-        if (!(p.dbg & 2)) gemv_finish<NB>(cur, W, K, rowmap, nu * RPU, xs, p.xs_stride, part, ring, pol);
-        else cp_async_wait<0>();
+        if (p.dbg & 2) cp_async_wait<0>();
+        else if (sb == 4) gemv_finish<NB, 4>(cur, W, K, rowmap, nrows, xs, p.xs_stride, part, ring, pol);
+        else if (sb == 2) gemv_finish<NB, 2>(cur, W, K, rowmap, nrows, xs, p.xs_stride, part, ring, pol);
+        else gemv_finish<NB, 1>(cur, W, K, rowmap, nrows, xs, p.xs_stride, part, ring, pol);
         __syncthreads();
         MK_TRACE(tr_li, tr_ph, 4);
+        MK_GT(tr_li, tr_ph * 3 + 1);
         for (int i = tid; i < nu * NB && !(p.dbg & 4); i += MK_THREADS) {
             const int j = i / NB, n = i % NB;
             float s[RPU];
@@ -311,6 +364,7 @@ __device__ __forceinline__ void gemv_phase(const StackParams& p, unsigned char* 
         __syncthreads();
     }
     MK_TRACE(tr_li, tr_ph, 5);
+    MK_GT(tr_li, tr_ph * 3 + 2);
 }
 
 // x = RMSNorm(src (+ add)) * w for every stream into shared memory; CTA 0 also stores the summed residual stream.
@@ -549,8 +603,9 @@ decode_stack_kernel(const __grid_constant__ StackParams p) {
         // ---- QKV: hn = h (+ pending MLP output); x = RMSNorm(hn); q,k,v = x W^T + b; RoPE; append
         gemv_phase<NB, 2>(p, smem, wqkv, D, qkv_p1 - qkv_p0, qkv_row,
             [&] {
-                if (li > 0) grid_barrier(p.sync, epoch, G);     // previous layer's down projection
+                if (li > 0) grid_wait(p.sync, epoch, G);     // previous layer's down projection
                 MK_TRACE(li, 0, 1);
+                MK_GT(li, 0);
                 if (!(p.dbg & 1)) preamble_norm<NB>(p, smem, hb0, li == 0, li == 0 ? nullptr : p.pending, ln1, hb1);
             },
             [&](int u, int n, const float (&s)[2]) {
@@ -591,10 +646,12 @@ decode_stack_kernel(const __grid_constant__ StackParams p) {
         //      (stream, kv head) merges the partials.  The first item's K/V tiles are requested before the barrier
         //      (they predate this step except for the newest row, which is fetched again afterwards).
         dp.layer = li;
+        grid_arrive(p.sync, epoch, G);
         if (c < n_items && warp < DWARPS)
             attn_item<1>(dp, c % p.n_splits, (c / p.n_splits) % Hkv, c / (p.n_splits * Hkv), smem, tid);
-        grid_barrier(p.sync, epoch, G);
+        grid_wait(p.sync, epoch, G);
         MK_TRACE(li, 1, 0);
+        MK_GT(li, 3);
         for (int item = c; item < n_items; item += G) {
             const int split = item % p.n_splits, kvh = (item / p.n_splits) % Hkv, b = item / (p.n_splits * Hkv);
             if (warp < DWARPS) {
@@ -618,24 +675,29 @@ decode_stack_kernel(const __grid_constant__ StackParams p) {
             __syncthreads();
         }
         MK_TRACE(li, 1, 5);
+        MK_GT(li, 5);
         MK_PHASE_DONE();
+        grid_arrive(p.sync, epoch, G);
 
         // ---- O projection
         gemv_phase<NB, 1>(p, smem, wo, Hq * HD, d_r1 - d_r0, d_row,
             [&] {
-                grid_barrier(p.sync, epoch, G);
+                grid_wait(p.sync, epoch, G);
                 MK_TRACE(li, 2, 1);
+                MK_GT(li, 6);
                 preamble_copy<NB>(p, smem, p.attn_out, Hq * HD);
             },
             [&](int u, int n, const float (&s)[1]) { p.o[(int64_t)n * D + d_r0 + u] = __float2bfloat16_rn(s[0]); },
             pol, li, 2);
         MK_PHASE_DONE();
+        grid_arrive(p.sync, epoch, G);
 
         // ---- gate/up: h2 = hn + o; x = RMSNorm(h2); act = silu(x Wg^T) * (x Wu^T)
         gemv_phase<NB, 2>(p, smem, wgu, D, i_r1 - i_r0, gu_row,
             [&] {
-                grid_barrier(p.sync, epoch, G);
+                grid_wait(p.sync, epoch, G);
                 MK_TRACE(li, 3, 1);
+                MK_GT(li, 9);
                 preamble_norm<NB>(p, smem, hb1, false, p.o, ln2, hb0);
             },
             [&](int u, int n, const float (&s)[2]) {
@@ -645,17 +707,20 @@ decode_stack_kernel(const __grid_constant__ StackParams p) {
             },
             pol, li, 3);
         MK_PHASE_DONE();
+        grid_arrive(p.sync, epoch, G);
 
         // ---- down projection -> pending (added to the residual stream by the next norm)
         gemv_phase<NB, 1>(p, smem, wd, I, d_r1 - d_r0, d_row,
             [&] {
-                grid_barrier(p.sync, epoch, G);
+                grid_wait(p.sync, epoch, G);
                 MK_TRACE(li, 4, 1);
+                MK_GT(li, 12);
                 preamble_copy<NB>(p, smem, p.act, I);
             },
             [&](int u, int n, const float (&s)[1]) { p.pending[(int64_t)n * D + d_r0 + u] = __float2bfloat16_rn(s[0]); },
             pol, li, 4);
         MK_PHASE_DONE();
+        grid_arrive(p.sync, epoch, G);
     }
 
     // ---- final norm, lm_head, greedy argmax (ties -> lowest index, as torch.argmax on these logits)
@@ -663,7 +728,7 @@ decode_stack_kernel(const __grid_constant__ StackParams p) {
     int best_i = 0x7FFFFFFF;
     gemv_phase<NB, 1>(p, smem, p.lm_head, D, v_r1 - v_r0, v_row,
         [&] {
-            grid_barrier(p.sync, epoch, G);
+            grid_wait(p.sync, epoch, G);
             preamble_norm<NB>(p, smem, hb0, false, p.pending, p.final_norm, nullptr);
         },
         [&](int u, int n, const float (&s)[1]) {
@@ -691,7 +756,8 @@ decode_stack_kernel(const __grid_constant__ StackParams p) {
             p.best_i[c * NB + tid] = bi;
         }
     }
-    grid_barrier(p.sync, epoch, G);
+    grid_arrive(p.sync, epoch, G);
+    grid_wait(p.sync, epoch, G);
     if (c == 0 && tid < NB) {
         float bv = -INFINITY;
         int bi = 0x7FFFFFFF;
@@ -834,25 +900,23 @@ int svln_decode_stack_step(const svln_kv_arena* arena, const svln_decode_stack* 
     p.off_part = (int)align_up((size_t)B * p.xs_stride * 2, 128);
     p.off_rowmap = p.off_part + MK_WARPS * MK_CAP * B * 4;
     p.off_ring = (int)align_up((size_t)p.off_rowmap + MK_CAP * 4, 128);
-    size_t misc = (size_t)p.off_ring + (size_t)MK_PIPE * 2 * MK_THREADS * 16;
+    size_t misc = (size_t)p.off_ring + (size_t)MK_RING_SLOTS * MK_THREADS * 16;
     if (misc < (size_t)DEC_SMEM) misc = DEC_SMEM;
     p.off_misc = (int)misc;
     const size_t smem = misc + MK_MISC;
     SVLN_REQUIRE(smem <= 227 * 1024, SVLN_ERR_RANGE, "svln_decode_stack_step: %zu bytes of shared memory needed", smem);
     static const int stop_env = getenv("SVLN_STACK_STOP") ? atoi(getenv("SVLN_STACK_STOP")) : 0;
     p.stop_after = stop_env;
-    static const int pf_env = getenv("SVLN_STACK_L2PF") ? atoi(getenv("SVLN_STACK_L2PF")) : 0;   // measured: no gain (the loop is not latency-bound), costs issue time
-    p.l2_prefetch = pf_env;
     static const int dbg_env = getenv("SVLN_STACK_DBG") ? atoi(getenv("SVLN_STACK_DBG")) : 0;
     p.dbg = dbg_env;
     static long long* trace_buf = nullptr;
     if (getenv("SVLN_STACK_TRACE") && !trace_buf) {
-        SVLN_CUDA(cudaMalloc(&trace_buf, ((size_t)(p.n_layer + 1) * 6 * 8 + 8) * sizeof(long long)));
-        SVLN_CUDA(cudaMemset(trace_buf, 0, ((size_t)(p.n_layer + 1) * 6 * 8 + 8) * sizeof(long long)));
+        SVLN_CUDA(cudaMalloc(&trace_buf, ((size_t)(p.n_layer + 1) * 6 * 8 + 8 + 160 * 16) * sizeof(long long)));
+        SVLN_CUDA(cudaMemset(trace_buf, 0, ((size_t)(p.n_layer + 1) * 6 * 8 + 8 + 160 * 16) * sizeof(long long)));
     }
     p.trace = trace_buf;
     g_trace_dev = trace_buf;
-    g_trace_n = (p.n_layer + 1) * 6 * 8 + 8;
+    g_trace_n = (p.n_layer + 1) * 6 * 8 + 8 + 160 * 16;
     static const int coop = getenv("SVLN_STACK_COOP") ? atoi(getenv("SVLN_STACK_COOP")) : 1;
 
     cudaStream_t st = (cudaStream_t)stream;

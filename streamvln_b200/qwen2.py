@@ -309,7 +309,8 @@ class Qwen2Engine:
         tok = self.argmax(logits)
         out = [tok]
         if max_new_tokens > 1:
-            runner = self._decode_runner(envs, use_graph and self.use_graphs)
+            # bench.py's profiling pass times the launches with CUDA events, which cannot sit inside a replayed graph
+            runner = self._decode_runner(envs, use_graph and self.use_graphs and self.prof is None)
             alive = None
             for _ in range(max_new_tokens - 1):
                 if eos_token_id is not None:
@@ -347,6 +348,18 @@ class Qwen2Engine:
             self._layer_ptrs = torch.tensor(rows, dtype=torch.int64).to(self.device)
         return self._layer_ptrs
 
+    def stack_step_bytes(self, kv_len: int) -> float:
+        """Algorithmic HBM bytes of one fused decode step of one stream: every decoder weight and the lm_head once
+        (the step is weight streaming), one embedding row, and the stream's K/V cache
+        (kv_bytes_per_token x cached length); activations are a few KB and ignored."""
+        cfg = self.cfg
+        if not hasattr(self, "_stack_weight_bytes"):
+            per_layer = sum(v.numel() * v.element_size() for v in self.w.layers[0].values())
+            self._stack_weight_bytes = (per_layer * cfg.num_hidden_layers + self.w.lm_head.numel() * 2 + self.w.final_norm.numel() * 2
+                                        + cfg.hidden_size * 2)
+        kv_per_tok = 2 * cfg.num_hidden_layers * cfg.num_key_value_heads * cfg.head_dim * 2
+        return float(self._stack_weight_bytes + kv_per_tok * kv_len)
+
     def _stack_desc(self, state: "_DecodeState", tok: torch.Tensor):
         """svln_decode_stack descriptor bound to this state's device tensors (built once per state)."""
         if state.stack is None:
@@ -383,7 +396,15 @@ class Qwen2Engine:
         if self.use_stack and tok.numel() <= self.STACK_MAX_STREAMS:
             d = self._stack_desc(state, tok)
             state.stack_tok_in.copy_(tok)
+            timed = self.prof is not None and not torch.cuda.is_current_stream_capturing()
+            if timed:
+                s_ev, e_ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s_ev.record()
             check(self.lib.svln_decode_stack_step(self.arena.ref, C.byref(d), cur_stream()))
+            if timed:
+                e_ev.record()
+                self.prof.setdefault("decode_stack", []).append((s_ev, e_ev, self.stack_step_bytes(state.host_len)))
+                state.host_len += 1
             self.launches += 1
             return state.stack_tok_out.clone()
         torch.sub(state.kv_len, 1, out=state.tok_pos)
@@ -410,6 +431,7 @@ class _DecodeState:
         self.tok_pos = torch.empty(B, dtype=torch.int32, device=dev)
         self.max_kv = eng.arena.max_len
         self.stack = None  # svln_decode_stack descriptor + its buffers (built on first use)
+        self.host_len = max([eng.arena.lens[e] for e in envs] + [0]) + 1   # host mirror of kv_len (profiling only)
 
 
 class _DecodeRunner:
