@@ -33,7 +33,7 @@ def launches(path):
     for k, t in rows:
         agg[k][0] += 1
         agg[k][1] += t
-    ours = ("attn_prefill", "attn_decode", "kv_", "rmsnorm", "swiglu", "argmax", "splice_rows", "gather_rows", "dedup", "voxel",
+    ours = ("attn_prefill", "attn_decode", "decode_stack", "gemv_kernel", "resample_", "kv_", "rmsnorm", "swiglu", "argmax", "splice_rows", "gather_rows", "dedup", "voxel",
             "compact_")
     print(f"{len(rows)} kernel launches, {tot / 1e3:.2f} ms of kernel time (ncu serialises launches and flushes caches: compare SHARES)\n")
     print("| kernel | launches | total us | avg us | share | ours |")
