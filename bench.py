@@ -35,7 +35,7 @@ METRIC = "streaming_nav_steps_per_sec"
 UNIT = "env_steps/s"
 ENV_STEPS_PER_TURN = 4
 N_GEN = 5
-PRIME_TURNS = 17
+PRIME_TURNS = 25
 # dram__bytes_read.sum + dram__bytes_write.sum of one decode_stack_kernel launch at the bench's shapes, from the
 # `ncu --set full` capture summarised under profiles/ (None until a capture exists)
 STACK_NCU_TRAFFIC_BYTES = 14_221_060_000   # profiles/r1_decode_stack_ncu_full.md: 14.2034 GB read + 17.65 MB written
@@ -105,7 +105,14 @@ def build_agent(device, mode: str):
 def run_turns(agent, n_turns: int, frames_host, frames_dev, resident: bool, geom=None):
     """n_turns model turns = 4*n_turns env steps through VLNEvaluator.step (the call a user makes)."""
     h2d = d2h = 0
+    verbose = os.environ.get("SVLN_BENCH_VERBOSE") == "1"
+    marks = []
     for _ in range(n_turns):
+        if verbose:
+            import torch
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            marks.append((agent.step_id, ev))
         for k in range(ENV_STEPS_PER_TURN):
             s = agent.step_id
             i = s % len(frames_host)
@@ -121,6 +128,11 @@ def run_turns(agent, n_turns: int, frames_host, frames_dev, resident: bool, geom
                 h2d += getattr(agent, "h2d_bytes", 0)
                 d2h += getattr(agent, "d2h_bytes", 0)
             agent.step_id += 1
+    if verbose and len(marks) > 1:
+        import torch
+        torch.cuda.synchronize()
+        print(("resident" if resident else "e2e") + " per-turn ms: " +
+              " ".join(f"{sid}:{a.elapsed_time(b):.1f}" for (sid, a), (_, b) in zip(marks[:-1], marks[1:])), file=sys.stderr, flush=True)
     return h2d, d2h
 
 
@@ -292,9 +304,10 @@ def main_ours(a):
     frames_dev = torch.stack([proc.preprocess(images=Image.fromarray(f), return_tensors="pt")["pixel_values"][0]
                               for f in frames_host]).to(device)
     K, W = a.steps, a.warmup
-    # ---- priming (initialisation, like building the model): one throw-away episode of two windows + one turn, so
+    # ---- priming (initialisation, like building the model): one throw-away episode of three windows + one turn, so
     #      every CUDA graph the steady state replays (vision, steady turn, window-start turn, decode) is captured
-    #      before any warm-up or timed step.  Graphs are captured on the second sighting of a shape.
+    #      AND replayed once before any warm-up or timed step.  Graphs are captured on the second sighting of a shape
+    #      (window starts: steps 32 and 64) and the first replay of a graph pays its upload (~16 ms, step 96).
     run_turns(agent, PRIME_TURNS, frames_host, frames_dev, True, geom)
     # ---- device-resident arm
     agent.reset_memory()
