@@ -102,7 +102,9 @@ __device__ __forceinline__ int4 lds128u(uint32_t addr) {
                  : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
     return r;
 }
-// 16-byte async copy global -> shared through L2 only; src_bytes = 0 zero-fills the destination
+// 16-byte async copy global -> shared through L2 only; src_bytes = 0 zero-fills the destination.  The evict_first
+// hint matters: without it the weight stream pushes the activations, K/V partials and barrier lines out of L2
+// and the whole step gets 12 % slower (measured).
 __device__ __forceinline__ void cp_async16_hint(uint32_t dst, const void* src, int src_bytes, uint64_t pol) {
     asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2, %3;"
                  ::"r"(dst), "l"(src), "r"(src_bytes), "l"(pol) : "memory");
@@ -165,11 +167,12 @@ constexpr int MK_RING_SLOTS = 24;                  // 4 KB ring slots (one lane-
 constexpr int MK_MAX_SB = 4;
 struct GemvCursor {
     int it, st, sup;                  // next step to issue: flat index, step within the super-block, super-block
-    const int4* p[MK_MAX_SB][2];      // row pointers (lane's 16 B of step 0) of rows g, g + 8 of each block, or null
+    const int4* p[MK_MAX_SB][2];      // where the lane's next 16 B of rows g, g + 8 of each block come from
+    int sz[MK_MAX_SB][2];             // 16, or 0 for a row that does not exist (the copy zero-fills its slot)
 };
 struct GemvGeom {
     const int4* Wv;
-    const int* rowmap;
+    const int* rowmap;      // [nrows] rows of this group, then (at MK_CAP) the balanced block starts [nblk + 1]
     int K8, nrows, nblk, nsup, nst, total, g;
     uint32_t slot0;
 };
@@ -203,11 +206,12 @@ __device__ __forceinline__ void gemv_set_super(GemvCursor& c, const GemvGeom& G)
 #pragma unroll
     for (int j = 0; j < SB; ++j) {
         const int blk = c.sup * SB + j;
-        c.p[j][0] = c.p[j][1] = nullptr;
+        c.p[j][0] = c.p[j][1] = G.Wv;
+        c.sz[j][0] = c.sz[j][1] = 0;
         if (blk < G.nblk) {
-            const int start = (blk * G.nrows) / G.nblk, size = ((blk + 1) * G.nrows) / G.nblk - start;
-            if (G.g < size) c.p[j][0] = G.Wv + (int64_t)G.rowmap[start + G.g] * G.K8;
-            if (G.g + 8 < size) c.p[j][1] = G.Wv + (int64_t)G.rowmap[start + G.g + 8] * G.K8;
+            const int start = G.rowmap[MK_CAP + blk], size = G.rowmap[MK_CAP + blk + 1] - start;
+            if (G.g < size) { c.p[j][0] = G.Wv + (int64_t)G.rowmap[start + G.g] * G.K8; c.sz[j][0] = 16; }
+            if (G.g + 8 < size) { c.p[j][1] = G.Wv + (int64_t)G.rowmap[start + G.g + 8] * G.K8; c.sz[j][1] = 16; }
         }
     }
 }
@@ -220,9 +224,8 @@ __device__ __forceinline__ void gemv_issue(GemvCursor& c, const GemvGeom& G, int
             if (j < nsb) {
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
-                    const int4* src = c.p[j][h];
-                    cp_async16_hint(G.slot0 + ((q * SB + j) * 2 + h) * MK_SLOT,
-                                    src ? (const void*)(src + c.st * MK_STEP) : (const void*)G.Wv, src ? 16 : 0, pol);
+                    cp_async16_hint(G.slot0 + ((q * SB + j) * 2 + h) * MK_SLOT, c.p[j][h], c.sz[j][h], pol);
+                    c.p[j][h] += MK_STEP;
                 }
             }
         }
@@ -243,7 +246,10 @@ __device__ __noinline__ GemvCursor gemv_start(const __nv_bfloat16* __restrict__ 
     GemvCursor c;
     c.it = c.st = c.sup = 0;
 #pragma unroll
-    for (int j = 0; j < MK_MAX_SB; ++j) c.p[j][0] = c.p[j][1] = nullptr;
+    for (int j = 0; j < MK_MAX_SB; ++j) {
+        c.p[j][0] = c.p[j][1] = nullptr;
+        c.sz[j][0] = c.sz[j][1] = 0;
+    }
     if (G.total > 0) gemv_set_super<SB>(c, G);
 #pragma unroll
     for (int q = 0; q < DEPTH; ++q) gemv_issue<SB>(c, G, q, pol);
@@ -288,7 +294,7 @@ __device__ __noinline__ void gemv_finish(GemvCursor c, const __nv_bfloat16* __re
                     for (int j = 0; j < SB; ++j) {
                         if (j < nsb) {
                             const int blk = c_sup * SB + j;
-                            const int start = (blk * nrows) / G.nblk, size = ((blk + 1) * nrows) / G.nblk - start;
+                            const int start = rowmap[MK_CAP + blk], size = rowmap[MK_CAP + blk + 1] - start;
                             float* dst = part + ((int64_t)warp * MK_CAP + start + g) * NB;
                             if (g < size) {
                                 if (2 * t < NB) dst[2 * t] = acc[j][0][0] + acc[j][1][0];
@@ -331,6 +337,10 @@ __device__ __forceinline__ void gemv_phase(const StackParams& p, unsigned char* 
     for (int u0 = 0; u0 < n_units; u0 += UPG) {
         const int nu = min(UPG, n_units - u0);
         for (int j = tid; j < nu * RPU; j += MK_THREADS) rowmap[j] = rowfn(u0 + j / RPU, j % RPU);
+        {
+            const int nr = nu * RPU, nb = (nr + 15) >> 4;
+            if (tid <= nb) rowmap[MK_CAP + tid] = (tid * nr) / nb;   // balanced blocks of <= 16 rows
+        }
         __syncthreads();
         const int nrows = nu * RPU, nblk = (nrows + 15) >> 4;
         const int sb = nblk >= 4 ? 4 : (nblk >= 2 ? 2 : 1);     // blocks advancing together (ILP) vs ring depth
@@ -899,7 +909,7 @@ int svln_decode_stack_step(const svln_kv_arena* arena, const svln_decode_stack* 
     p.xs_stride = kmax + MK_XPAD;
     p.off_part = (int)align_up((size_t)B * p.xs_stride * 2, 128);
     p.off_rowmap = p.off_part + MK_WARPS * MK_CAP * B * 4;
-    p.off_ring = (int)align_up((size_t)p.off_rowmap + MK_CAP * 4, 128);
+    p.off_ring = (int)align_up((size_t)p.off_rowmap + (MK_CAP + MK_CAP / 16 + 2) * 4, 128);
     size_t misc = (size_t)p.off_ring + (size_t)MK_RING_SLOTS * MK_THREADS * 16;
     if (misc < (size_t)DEC_SMEM) misc = DEC_SMEM;
     p.off_misc = (int)misc;
