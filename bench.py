@@ -54,18 +54,63 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe).  NVML is polled from a
+    thread of this process (nvidia_ml_py): spawning `nvidia-smi -lms` at the start of the timed region and its
+    periodic driver queries cost the first timed turns 3-12 ms each (measured); nvidia-smi is the fallback."""
 
-    def __init__(self, gpu_index: int):
-        self.rows, self.proc = [], None
-        self.cmd = ["nvidia-smi", f"--id={gpu_index}",
-                    "--query-gpu=clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-                    "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-                    "clocks_event_reasons.sw_power_cap", "--format=csv,noheader,nounits", "-lms", "200"]
+    _BITS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+
+    def __init__(self, gpu_index: int, period_s: float = 0.05):
+        self.idx, self.period = gpu_index, period_s
+        self.sm, self.mx, self.reasons = [], [], set()
+        self.thread = self.proc = self.nvml = self.handle = None
+        self.stop_flag = threading.Event()
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            # CUDA_VISIBLE_DEVICES remaps indices: go through the PCI bus id of the torch device
+            import torch
+
+            bus = torch.cuda.get_device_properties(gpu_index).pci_bus_id if hasattr(torch.cuda.get_device_properties(gpu_index), "pci_bus_id") else None
+            self.handle = (pynvml.nvmlDeviceGetHandleByIndex(gpu_index) if bus is None else None)
+            if self.handle is None:
+                n = pynvml.nvmlDeviceGetCount()
+                for i in range(n):
+                    h = pynvml.nvmlDeviceGetHandleByIndex(i)
+                    if int(pynvml.nvmlDeviceGetPciInfo(h).bus) == int(bus):
+                        self.handle = h
+                        break
+                if self.handle is None:
+                    self.handle = pynvml.nvmlDeviceGetHandleByIndex(min(gpu_index, n - 1))
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _poll(self):
+        nv = self.nvml
+        while not self.stop_flag.is_set():
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)))
+                self.mx.append(float(nv.nvmlDeviceGetMaxClockInfo(self.handle, nv.NVML_CLOCK_SM)))
+                mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+                self.reasons |= {name for bit, name in self._BITS.items() if mask & bit}
+            except Exception:
+                pass
+            self.stop_flag.wait(self.period)
 
     def start(self):
+        if self.nvml is not None:
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        cmd = ["nvidia-smi", f"--id={self.idx}",
+               "--query-gpu=clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+               "clocks_event_reasons.sw_power_cap", "--format=csv,noheader,nounits", "-lms", "200"]
         try:
-            self.proc = subprocess.Popen(self.cmd, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.rows = []
+            self.proc = subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
             self.proc = None
@@ -75,6 +120,11 @@ class ClockSampler:
             self.rows.append([x.strip() for x in line.split(",")])
 
     def stop(self):
+        if self.thread is not None:
+            self.stop_flag.set()
+            self.thread.join(timeout=1.0)
+            return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": max(self.mx) if self.mx else None,
+                    "reasons": sorted(self.reasons), "samples": len(self.sm), "source": "nvml"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.25)
@@ -84,7 +134,7 @@ class ClockSampler:
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(sm)}
+                "samples": len(sm), "source": "nvidia-smi"}
 
 
 # ------------------------------------------------------------------------------------------ ours
@@ -304,11 +354,14 @@ def main_ours(a):
     frames_dev = torch.stack([proc.preprocess(images=Image.fromarray(f), return_tensors="pt")["pixel_values"][0]
                               for f in frames_host]).to(device)
     K, W = a.steps, a.warmup
-    # ---- priming (initialisation, like building the model): one throw-away episode of three windows + one turn, so
-    #      every CUDA graph the steady state replays (vision, steady turn, window-start turn, decode) is captured
-    #      AND replayed once before any warm-up or timed step.  Graphs are captured on the second sighting of a shape
-    #      (window starts: steps 32 and 64) and the first replay of a graph pays its upload (~16 ms, step 96).
-    run_turns(agent, PRIME_TURNS, frames_host, frames_dev, True, geom)
+    # ---- priming (initialisation, like building the model): throw-away episodes so that every CUDA graph the
+    #      steady state replays (vision, steady turn, window-start turns, decode) is captured AND replayed once
+    #      before any warm-up or timed step.  A graph is captured on the second sighting of a shape and its first
+    #      replay pays the upload (~12-16 ms).  The first window start of an episode (step 32) and the later ones
+    #      (64, 96, ...) are different shapes, hence two episodes of three windows and a third of one.
+    for n in (PRIME_TURNS, PRIME_TURNS, 9):
+        agent.reset_memory()
+        run_turns(agent, n, frames_host, frames_dev, True, geom)
     # ---- device-resident arm
     agent.reset_memory()
     run_turns(agent, W, frames_host, frames_dev, True, geom)
