@@ -244,6 +244,14 @@ int svln_gemv(const void* W, const void* x, const void* bias, void* out, int M, 
 int svln_argmax(const void* logits, int is_f32, int64_t n_rows, int64_t vocab,
                 int64_t* out_idx, svln_stream_t stream);
 
+/* Bilinear token pooling of the projected vision features: feat [n_frames, grid_in^2, dim] bf16 ->
+ * out [n_frames, grid_out^2, dim] bf16.  Replaces StreamVLNForCausalLM.get_2dPool with mm_spatial_pool_mode
+ * "bilinear" (streamvln/model/stream_video_vln.py:53-73: permute to NCHW, F.interpolate(size=grid_out, bilinear,
+ * align_corners=False), permute back; grid_out = ceil(grid_in / 2) = 14 for the 27 x 27 SigLIP grid) with ATen's
+ * arithmetic in fp32. */
+int svln_pool_bilinear(const void* feat, int n_frames, int grid_in, int grid_out, int dim, void* out,
+                       svln_stream_t stream);
+
 /* ----------------------------------------------------------------------------------------
  * Fused decode stack: one persistent launch = one greedy decode step of ONE stream (n_stream = 1)
  * (embedding row -> n_layer x [RMSNorm, QKV + bias + RoPE + append to the arena, split-KV attention, O,

@@ -91,6 +91,7 @@ PROTOTYPES = {
     "svln_swiglu": (_i, [_vp, _i64, _i, _vp, _vp]),
     "svln_gemv": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "svln_argmax": (_i, [_vp, _i, _i64, _i64, _vp, _vp]),
+    "svln_pool_bilinear": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
     "svln_decode_stack_workspace_bytes": (C.c_size_t, [C.POINTER(DecodeStackStruct)]),
     "svln_decode_stack_status": (_i, [C.POINTER(DecodeStackStruct), _vp, _vp]),
     "svln_decode_stack_trace": (_i, [_vp, _i]),

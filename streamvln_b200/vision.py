@@ -197,6 +197,17 @@ class VisionFrontEnd(torch.nn.Module):
 def pool_2d(x: torch.Tensor, side: int, stride: int = 2, mode: str = "bilinear") -> torch.Tensor:
     """get_2dPool (stream_video_vln.py:53-73): [F, side*side, D] -> [F, side'^2, D]."""
     Fn, _, D = x.shape
+    if mode == "bilinear" and x.is_cuda and x.dtype == torch.bfloat16 and D % 8 == 0:
+        # svln_pool_bilinear: ATen's bilinear arithmetic on the token-major layout (torch's NCHW kernel takes 2 ms
+        # per frame at D = 3584, more than the rest of the vision front end)
+        from . import _lib
+
+        lib = _lib.load()
+        side_out = math.ceil(side / stride)
+        x = x.contiguous()
+        out = torch.empty(Fn, side_out * side_out, D, dtype=x.dtype, device=x.device)
+        _lib.check(lib.svln_pool_bilinear(_lib.ptr(x), Fn, side, side_out, D, _lib.ptr(out), _lib.cur_stream()))
+        return out
     x = x.view(Fn, side, side, D).permute(0, 3, 1, 2).contiguous()
     if mode == "average":
         x = F.avg_pool2d(x, stride)

@@ -277,3 +277,22 @@ def test_gpu_image_processor_matches_pil(svln_lib, cuda):
         for i in range(2):
             want = proc.preprocess(images=Image.fromarray(frames[i]), return_tensors="pt")["pixel_values"][0]
             assert torch.equal(got[i], want), (h, w, i)
+
+
+def test_pool_bilinear_kernel_matches_reference_pool(svln_lib, cuda):
+    """svln_pool_bilinear vs the oracle's get_2dPool restatement (CPU F.interpolate, pinned against the reference's own
+    code by tests/golden/ref_glue_*.npz), for the SigLIP grid and the sweep grids.  Floating point: at most one bf16
+    ulp (2^-7 relative) on at most 2e-4 of the elements - ATen's fused-multiply-add pattern is not reproducible."""
+    from streamvln_b200.vision import pool_2d
+
+    g = torch.Generator().manual_seed(5)
+    for side, dim, frames in ((27, 3584, 2), (27, 256, 9), (24, 512, 1), (20, 64, 3), (14, 128, 2), (5, 8, 1)):
+        x = (torch.randn(frames, side * side, dim, generator=g) * 3).bfloat16()
+        want = glue.pool_2d(x, side, 2, "bilinear")                     # bf16 in, fp32 opmath, bf16 out
+        got = pool_2d(x.to(cuda), side, 2, "bilinear").cpu()
+        assert got.shape == want.shape == (frames, ((side + 1) // 2) ** 2, dim)
+        diff = (got.float() - want.float()).abs()
+        assert float((diff > 0).float().mean()) <= 2e-4, (side, dim, float((diff > 0).float().mean()))
+        bound = torch.maximum(want.float().abs(), got.float().abs()) * 2.0 ** -7   # one ulp of the larger binade
+        # + an absolute floor for results that are tiny by cancellation (fp32 rounding of operands of magnitude ~10)
+        assert bool((diff <= bound * 1.001 + 1e-5).all()), (side, dim, float(diff.max()))
