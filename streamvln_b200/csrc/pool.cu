@@ -6,8 +6,8 @@
 // channels of one output token and reads the four source tokens with 128-bit loads: 5.2 MB in, 1.4 MB out.
 // Arithmetic follows ATen's (align_corners = False, fp32 opmath, scale = gin / gout as a float division,
 // src = max(0, fma(scale, dst + 0.5, -0.5)), lambda1 = src - floor(src)):
-// out = l0h * (l0w * x00 + l1w * x01) + l1h * (l0w * x10 + l1w * x11), rounded to bf16 once.  Against the CPU
-// F.interpolate the oracle uses this differs by one bf16 ulp on ~5e-5 of the elements (ATen's exact contraction
+// out = l0h * (l0w * x00 + l1w * x01) + l1h * (l0w * x10 + l1w * x11), rounded to bf16 once.  Against CPU
+// F.interpolate (what the parity tests compare with) this differs by one bf16 ulp on ~5e-5 of the elements (ATen's exact contraction
 // pattern is not reproducible from outside); the test bounds both the rate and the size of those flips.
 #include "svln_common.cuh"
 
