@@ -80,6 +80,19 @@ def bench_kv_attn(device, pk, n_env=64, L=3000, n_new=217) -> Dict:
     ms = _time(lambda: ar.append_rope(3, qkv, Hq, tok_env, tok_pos, q_out))
     rows.append(_row("kv_append_rope_kernel", "hbm", 2 * n_tok * (Hq + 2 * Hkv) * hd * 2, ms, pk["hbm_gbs"], "GB/s",
                      f"{n_env} streams x {n_new} tokens, one layer; read qkv + write q/K/V"))
+    del qkv, q_out
+    # the same kernel at the window-start shape (9 views x 196 tokens + text per stream): 0.9 GB per launch
+    n_ws = 1900
+    ws_env = max(1, n_env // 4)
+    n_tok = ws_env * n_ws
+    qkv = torch.randn(n_tok, (Hq + 2 * Hkv) * hd, device=device, dtype=torch.bfloat16)
+    tok_env_w = torch.arange(ws_env, device=device, dtype=torch.int32).repeat_interleave(n_ws)
+    tok_pos_w = torch.arange(n_ws, device=device, dtype=torch.int32).repeat(ws_env)
+    q_out = torch.empty(n_tok, Hq, hd, device=device, dtype=torch.bfloat16)
+    ms = _time(lambda: ar.append_rope(3, qkv, Hq, tok_env_w, tok_pos_w, q_out))
+    rows.append(_row("kv_append_rope_kernel, window start", "hbm", 2 * n_tok * (Hq + 2 * Hkv) * hd * 2, ms, pk["hbm_gbs"], "GB/s",
+                     f"{ws_env} streams x {n_ws} tokens, one layer; read qkv + write q/K/V"))
+    del qkv, q_out
     # eviction + compaction with re-rotation: drop one 221-row turn and a third of a 1568-row memory region
     P, M, turn = 60, 1568, 221
     keep_mem = torch.arange(M)[torch.arange(M) % 3 != 0]
