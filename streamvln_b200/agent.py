@@ -208,6 +208,10 @@ class VLNEvaluator:
         self.output_ids = outputs.sequences
         ids_host = self.output_ids.cpu()  # the D2H read of the turn's result
         self.d2h_bytes = ids_host.numel() * 8
+        if ids_host.numel() and int(ids_host.min()) < 0:
+            # svln_decode_stack_step reports token -1 when one of its grid barriers timed out (include/svln.h)
+            raise RuntimeError("libsvln: the fused decode stack aborted (grid barrier timeout); "
+                               "svln_decode_stack_status() has the barrier index")
         llm_outputs = self.tokenizer.batch_decode(ids_host, skip_special_tokens=False)[0].strip()
         self.past_key_values = outputs.past_key_values
         action_seq = self.parse_actions(llm_outputs)

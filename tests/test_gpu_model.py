@@ -124,6 +124,40 @@ def test_fused_decode_stack_matches_hf(tiny, cuda):
         eng._graphs.clear()
 
 
+@pytest.mark.parametrize("n_ctx", [1, 63, 64, 65, 1000])
+def test_fused_decode_stack_context_lengths(tiny, cuda, n_ctx):
+    """Edge cases of the in-kernel split-KV attention: a cache shorter than one split, exactly on / around a tile
+    boundary, and many tiles; logits of every step within the tolerance of stock transformers."""
+    from transformers import DynamicCache
+    from streamvln_b200.qwen2 import Chunk
+
+    m, lm = tiny
+    eng = m.engine
+    g = torch.Generator().manual_seed(100 + n_ctx)
+    emb = (torch.randn(n_ctx, m.config.llm.hidden_size, generator=g) * 0.05).bfloat16()
+    eng.keep_decode_logits = True
+    eng._graphs.clear()
+    try:
+        eng.arena.reset_env(0)
+        tok = eng.forward(emb.clone().to(cuda), [Chunk(0, 0, n_ctx, n_ctx)]).argmax(-1)
+        c0 = DynamicCache(config=lm.config)
+        with torch.no_grad():
+            lm(inputs_embeds=emb[None].float(), past_key_values=c0, use_cache=True)
+        runner = eng._decode_runner([0], True)
+        for _ in range(3):
+            fed = tok.clone()
+            tok = runner.step(tok)
+            with torch.no_grad():
+                want = lm(input_ids=fed.cpu()[None], past_key_values=c0, use_cache=True).logits[0, -1]
+            assert int(tok) >= 0, "a grid barrier of the fused stack timed out"
+            assert _rel(runner.graph.state.stack_logits[0].cpu(), want) <= TOL
+        runner.finish()
+        assert eng.arena.lens[0] == c0.get_seq_length() == n_ctx + 3
+    finally:
+        eng.keep_decode_logits = False
+        eng._graphs.clear()
+
+
 def test_fused_decode_stack_agrees_with_launch_per_op_path(tiny, cuda):
     """Same state, same fed tokens: every token the unfused kernel sequence picks is greedy (up to a near-tie
     margin: accumulation orders differ) under the fused stack's fp32 logits."""
