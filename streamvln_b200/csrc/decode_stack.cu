@@ -28,7 +28,8 @@
 // it: 1.3 TB/s); a 20-deep ring (30 % slower than 8-12 steps); bulk or per-line L2 prefetch of the next phase
 // and page-touching one phase ahead (no gain: the main loops are HBM-bound, gate/up streams at 6.9 TB/s);
 // fencing after the weight prologue (the fence waits for the copies: +3-6 us per barrier); 512-byte coalesced
-// requests instead of 8 rows x 64 B (35 % slower in DRAM).
+// requests instead of 8 rows x 64 B (35 % slower in DRAM); no L2 evict_first hint on the weight copies (12 % slower);
+// an 8-warp attention item with the O projection's weights streaming behind it (5 % slower).
 // Rounding points are those of the unfused path (fused_ops.cu, kv_window.cu rope8, gemv.cu), i.e. HF's bf16
 // modules; accumulation order differs from cuBLAS, which the parity tolerance (1e-2 on logits) covers.
 #include <stdlib.h>
@@ -40,7 +41,11 @@ namespace svln {
 constexpr int MK_WARPS = 8;
 constexpr int MK_THREADS = MK_WARPS * 32;
 constexpr int MK_CAP = 304;          // rows per group (multiple of 16; gate/up pairs of one CTA at 7B: 2 x 128)
-constexpr int MK_MAX_B = 1;           // the NB = 2 instantiation faults on 7B shapes (unresolved): kept out of the ABI
+// The kernel is written for NB <= 2 streams, but only NB = 1 is instantiated: in the NB = 2 build ptxas 12.9 selects,
+// for some of the weight copies, an LDGSTS form ([R+UR0], desc[UR1]) that does not reference the cache-policy
+// descriptor registers it has just loaded and raises "Warp Illegal Instruction" on the B200 (pinned down with
+// cuda-gdb; laundering the address, a 64-bit shared operand and creating the policy locally did not avoid it).
+constexpr int MK_MAX_B = 1;
 constexpr int MK_MAX_SPLITS = 32;
 constexpr int MK_XPAD = 32;          // elements between the x rows of two streams: 64 B, spreads the banks
 constexpr int MK_MISC = 4096;        // bytes of misc shared memory (reductions, flags, combine weights)
