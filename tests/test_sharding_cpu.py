@@ -119,3 +119,20 @@ def test_synth_geometry_conventions():
     assert np.allclose(P[:3, 3], [1.0, -2.0, 1.25])
     a, poses = synth.action_walk(50, np.random.default_rng(0))
     assert set(a.tolist()) <= {1, 2, 3} and poses.shape == (50, 4, 4)
+
+
+def test_no_misencoded_ldgsts_in_the_library():
+    """ptxas 12.9 has emitted (in a two-stream build of decode_stack.cu) LDGSTS instructions whose cache-policy
+    descriptor operand is an odd uniform register (`desc[UR1]`): the B200 raises "Warp Illegal Instruction" on them.
+    Guard the shipped library against that codegen fault (no GPU needed: cuobjdump reads the cubin)."""
+    import re
+    import shutil
+    import subprocess
+    from streamvln_b200 import _lib
+
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not Path(cuobjdump).exists():
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([cuobjdump, "-sass", str(_lib.LIB_PATH)], capture_output=True, text=True, check=True).stdout
+    bad = [l.strip() for l in sass.splitlines() if "LDGSTS" in l and re.search(r"desc\[UR\d*[13579]\]", l)]
+    assert not bad, bad[:3]
