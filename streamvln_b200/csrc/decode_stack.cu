@@ -821,6 +821,8 @@ static int stack_grid() {
 }
 
 static int stack_splits(int G, int B, int Hkv) {
+    static const int s_env = getenv("SVLN_STACK_SPLITS") ? atoi(getenv("SVLN_STACK_SPLITS")) : 0;
+    if (s_env >= 1 && s_env <= MK_MAX_SPLITS && s_env * B * Hkv <= G) return s_env;
     int s = G / (B * Hkv);
     if (s < 1) s = 1;
     if (s > MK_MAX_SPLITS) s = MK_MAX_SPLITS;
