@@ -38,7 +38,7 @@ N_GEN = 5
 PRIME_TURNS = 25
 # dram__bytes_read.sum + dram__bytes_write.sum of one decode_stack_kernel launch at the bench's shapes, from the
 # `ncu --set full` capture summarised under profiles/ (None until a capture exists)
-STACK_NCU_TRAFFIC_BYTES = 14_221_060_000   # profiles/r1_decode_stack_ncu_full.md: 14.2034 GB read + 17.65 MB written
+STACK_NCU_TRAFFIC_BYTES = 14_221_525_000   # profiles/r1_decode_stack_ncu_full.md: 14.2037 GB read + 17.87 MB written
 INSTRUCTION = ("walk down the hallway past the kitchen turn left at the sofa go through the second door on the right "
                "and wait by the window next to the wooden table in the corner of the bedroom then stop near the bed "
                "facing the large mirror on the wall")  # 48 words ~ the 40 fixed token ids of SURVEY §8d
