@@ -52,7 +52,7 @@ __device__ __forceinline__ void rope8(const int4& lo, const int4& hi, const int4
     }
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 8)
 kv_append_rope_kernel(svln_kv_arena arena, int layer, const int4* __restrict__ qkv, int n_q_head,
                       const int32_t* __restrict__ tok_env, const int32_t* __restrict__ tok_pos, int n_tok,
                       const int4* __restrict__ cos_t, const int4* __restrict__ sin_t, int n_pos,
@@ -65,7 +65,7 @@ kv_append_rope_kernel(svln_kv_arena arena, int layer, const int4* __restrict__ q
     const int env = tok_env[tok], pos = tok_pos[tok];
     if (env < 0 || env >= arena.n_env || pos < 0 || pos >= arena.max_len || pos >= n_pos) return;
     const int4* src = qkv + ((int64_t)tok * heads + h) * 16;
-    const int4 lo = src[j], hi = src[8 + j];
+    const int4 lo = ld_stream(src + j), hi = ld_stream(src + 8 + j);   // the GEMM output is read exactly once
     int4* dst;
     bool rotate = true;
     if (h < n_q_head) {
