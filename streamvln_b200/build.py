@@ -34,6 +34,7 @@ def _digest() -> str:
         h.update(f.name.encode())
         h.update(f.read_bytes())
     h.update(" ".join(NVCC_FLAGS).encode())
+    h.update(os.environ.get("SVLN_NVCC_EXTRA", "").encode())
     return h.hexdigest()
 
 
@@ -46,9 +47,10 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     obj_dir.mkdir(exist_ok=True)
     objs = []
     procs = []
+    extra = os.environ.get("SVLN_NVCC_EXTRA", "").split()   # e.g. -DSVLN_PF_INSTRUMENT for the prefill trace hooks
     for src in _sources():
         obj = obj_dir / (src.stem + ".o")
-        cmd = [nvcc, *NVCC_FLAGS, "-c", str(src), "-o", str(obj)]
+        cmd = [nvcc, *NVCC_FLAGS, *extra, "-c", str(src), "-o", str(obj)]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(str(obj))
     log = []

@@ -34,7 +34,7 @@ constexpr int S3_XCH = S3_BAR + 256;                 // float [2][2][128] row-ma
 constexpr int P3_SMEM = S3_XCH + 2 * 2 * 128 * 4;
 
 enum { B3_K_FULL = 0, B3_K_EMPTY = 3, B3_V_FULL = 6, B3_V_EMPTY = 9, B3_S_FULL = 12, B3_P_FULL = 14, B3_PV_DONE = 16,
-       B3_COUNT = 18 };
+       B3_Q_FULL = 18, B3_COUNT = 19 };
 
 struct Prefill3Params {
     const __nv_bfloat16* q;
@@ -67,6 +67,20 @@ struct Prefill3Params {
         if (p.trace && blockIdx.x == gridDim.x / 2 && blockIdx.y == 0 && blockIdx.z == 0 && (tile) < 32 && lane == 0) \
             p.trace[((role) * 32 + (tile)) * 8 + (slot)] = clock64();                                        \
     } while (0)
+#endif
+// every CTA's lifetime (instrumented builds): [cta][4] = smid, globaltimer at entry, after the Q store, at exit
+#ifdef SVLN_PF_INSTRUMENT
+#define P3_LIFE(slot_)                                                                                       \
+    do {                                                                                                     \
+        if (p.trace && threadIdx.x == 0) {                                                                   \
+            unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                    \
+            unsigned sm_; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm_));                                   \
+            long long* d_ = p.trace + 4 * 32 * 8 + ((int64_t)(blockIdx.y * gridDim.x + blockIdx.x)) * 4;     \
+            d_[0] = sm_; d_[slot_] = (long long)t_;                                                          \
+        }                                                                                                    \
+    } while (0)
+#else
+#define P3_LIFE(slot_) do { } while (0)
 #endif
 
 // D[tmem] (+)= A[tmem] * B[smem]
@@ -108,6 +122,7 @@ attn_prefill3_kernel(const __grid_constant__ CUtensorMap kv_map, const __grid_co
     auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    P3_LIFE(1);
     const int kvh = blockIdx.y;
     const int g = p.n_q_head / p.n_kv_head;
     const int gtile = (int)gridDim.x - 1 - (int)blockIdx.x;   // heaviest (latest rows) first
@@ -138,32 +153,14 @@ attn_prefill3_kernel(const __grid_constant__ CUtensorMap kv_map, const __grid_co
     const int plane_k = ((env * p.n_layer + p.layer) * 2 + 0) * p.n_kv_head + kvh;
     const int plane_v = plane_k + p.n_kv_head;
 
-    if (tid == 0) {
-        for (int i = 0; i < 12; ++i) mbar_init(BAR(i), 1);
-        if (CLUSTER)   // a stage is free only when BOTH CTAs' tensor cores are done with it
-            for (int i = 0; i < 3; ++i) { mbar_init(BAR(B3_K_EMPTY + i), 2); mbar_init(BAR(B3_V_EMPTY + i), 2); }
-        mbar_init(BAR(B3_S_FULL), 1); mbar_init(BAR(B3_S_FULL + 1), 1);
-        mbar_init(BAR(B3_P_FULL), P3_SOFTMAX_WARPS); mbar_init(BAR(B3_P_FULL + 1), P3_SOFTMAX_WARPS);
-        mbar_init(BAR(B3_PV_DONE), 1); mbar_init(BAR(B3_PV_DONE + 1), 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(s2u(tmem_ptr_smem)) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (CLUSTER) cluster_sync_all();   // the partner's barriers are initialised before anything is multicast into them
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_ptr_smem;
-    const uint32_t TM_S0 = tmem_base, TM_O = tmem_base + 256, TM_Q = tmem_base + 384;
-
-    // Q tile -> TMEM as the A operand: lane = row, 32-bit column c = dims (2c, 2c+1).  Softmax mapping:
-    // row 32*(warp%4)+lane, dims [64*half, 64*half+64) = columns [32*half, 32*half+32).
+    // Prologue, overlapped: the Q rows are requested first (registers only), then barriers and tensor memory are set
+    // up while they fly; after the one CTA barrier the TMA warp starts streaming K/V at once, the softmax warps move
+    // Q into TMEM and signal Q_FULL, and only the MMA warp waits for it.  (Measured before: 4.1 us from CTA entry to
+    // "Q stored" with these steps in sequence, of the 8.4 us a CTA spends outside its key loop.)
+    uint32_t qv[32];
     if (warp < P3_SOFTMAX_WARPS) {
         const int r = (warp & 3) * 32 + lane, half = warp >> 2;
         const int R = row0 + r;
-        uint32_t qv[32];
         if (r < rows_here) {
             const int tq = R / g, hg = R - tq * g;
             const int4* src = reinterpret_cast<const int4*>(p.q + ((int64_t)(qs + tq) * p.n_q_head + kvh * g + hg) * P3_HD) + half * 8;
@@ -176,12 +173,39 @@ attn_prefill3_kernel(const __grid_constant__ CUtensorMap kv_map, const __grid_co
 #pragma unroll
             for (int c = 0; c < 32; ++c) qv[c] = 0u;
         }
-        tmem_st32(TM_Q + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(half * 32), qv);
-        tmem_wait_st();
+    }
+    if (tid == 0) {
+        for (int i = 0; i < 12; ++i) mbar_init(BAR(i), 1);
+        if (CLUSTER)   // a stage is free only when BOTH CTAs' tensor cores are done with it
+            for (int i = 0; i < 3; ++i) { mbar_init(BAR(B3_K_EMPTY + i), 2); mbar_init(BAR(B3_V_EMPTY + i), 2); }
+        mbar_init(BAR(B3_S_FULL), 1); mbar_init(BAR(B3_S_FULL + 1), 1);
+        mbar_init(BAR(B3_P_FULL), P3_SOFTMAX_WARPS); mbar_init(BAR(B3_P_FULL + 1), P3_SOFTMAX_WARPS);
+        mbar_init(BAR(B3_PV_DONE), 1); mbar_init(BAR(B3_PV_DONE + 1), 1);
+        mbar_init(BAR(B3_Q_FULL), P3_SOFTMAX_WARPS);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == P3_SOFTMAX_WARPS) {   // the MMA warp allocates: the softmax warps have loads in flight
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(s2u(tmem_ptr_smem)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
     __syncthreads();
+    if (CLUSTER) cluster_sync_all();   // the partner's barriers are initialised before anything is multicast into them
     tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+    const uint32_t TM_S0 = tmem_base, TM_O = tmem_base + 256, TM_Q = tmem_base + 384;
+    P3_LIFE(2);
+
+    // Q tile -> TMEM as the A operand: lane = row, 32-bit column c = dims (2c, 2c+1).  Softmax mapping:
+    // row 32*(warp%4)+lane, dims [64*half, 64*half+64) = columns [32*half, 32*half+32).
+    if (warp < P3_SOFTMAX_WARPS) {
+        const int half = warp >> 2;
+        tmem_st32(TM_Q + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(half * 32), qv);
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(BAR(B3_Q_FULL));
+    }
 
     if (warp == P3_SOFTMAX_WARPS + 1) {
         // ------------------------------------------------------------ TMA producer (uniform warp, elected lane)
@@ -239,6 +263,8 @@ attn_prefill3_kernel(const __grid_constant__ CUtensorMap kv_map, const __grid_co
         // S buffer bf is rewritten by QK(j+2) only after PV(j) (which read P(j) from it) was ISSUED: the tensor
         // pipe runs in order, so no extra barrier is needed; PV(j) itself waits for P_FULL(j), i.e. for every
         // softmax thread to be done with S(j).
+        mbar_wait(BAR(B3_Q_FULL), 0);   // Q is in tensor memory
+        tc_fence_after();
         if (n_tiles > 0) issue_qk(0);
         for (int j = 0; j < n_tiles; ++j) {
             if (j + 1 < n_tiles) issue_qk(j + 1);
@@ -403,7 +429,257 @@ attn_prefill3_kernel(const __grid_constant__ CUtensorMap kv_map, const __grid_co
         tc_fence_before();
     }
     __syncthreads();
+    P3_LIFE(3);
     if (CLUSTER) cluster_sync_all();   // neither CTA may exit while the partner can still multicast / commit into it
+    if (warp == P3_SOFTMAX_WARPS) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+    }
+}
+
+// ---- wide variant: 16 softmax warps -----------------------------------------------------------------------------
+// Measured on the kernel above: time = 0.97 us x key tiles + 8.4 us per CTA, and a persistent version (one CTA per SM
+// walking a list of items, K/V streaming across items) kept the same 7.6 us per ITEM - the fixed cost is pipeline
+// fill/drain, not CTA launch - and 1.0 us (1900 cycles) per tile against 1024 cycles of MMA work: the eight softmax
+// warps are the critical path (64 scores per thread per tile: TMEM load, max, exchange, exp2, pack, TMEM store).
+// Here four warps share each TMEM lane quadrant and take 32 score columns each, so a thread handles 32 scores per
+// tile; the row max / row sum are exchanged among the four through shared memory and one 128-thread named barrier.
+constexpr int PW_SOFTMAX_WARPS = 16;
+constexpr int PW_THREADS = (PW_SOFTMAX_WARPS + 2) * 32;
+constexpr int SW_XCH = S3_BAR + 256;                      // float [2][4][128] row-max exchange
+constexpr int SW_XCH2 = SW_XCH + 2 * 4 * 128 * 4;         // float [4][128] row-sum exchange
+constexpr int PW_SMEM = SW_XCH2 + 4 * 128 * 4;
+
+__global__ void __launch_bounds__(PW_THREADS, 1)
+attn_prefill3w_kernel(const __grid_constant__ CUtensorMap kv_map, const __grid_constant__ Prefill3Params p) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const uint32_t sbase = s2u(smem);
+    if ((sbase & 1023u) != 0) __trap();
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + S3_BAR + B3_COUNT * 8);
+    const uint32_t bar0 = sbase + S3_BAR;
+    auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int kvh = blockIdx.y;
+    const int g = p.n_q_head / p.n_kv_head;
+    const int gtile = (int)gridDim.x - 1 - (int)blockIdx.x;   // heaviest (latest rows) first
+    int b = 0;
+    while (b + 1 < p.n_seq && gtile >= p.tile_start[b + 1]) ++b;
+    const int mtile = gtile - p.tile_start[b];
+    const bool dev = p.d_env != nullptr;
+    const int nq = dev ? p.d_n_q[b] : p.n_q[b];
+    const int len = dev ? p.d_kv_len[b] : p.kv_len[b];
+    const int env = dev ? p.d_env[b] : p.env[b];
+    const int qs = dev ? p.d_q_start[b] : p.q_start[b];
+    const int rows_total = nq * g;
+    const int row0 = mtile * P3_BM;
+    const int rows_here = min(P3_BM, rows_total - row0);
+    const int tq_last = (row0 + rows_here - 1) / g;
+    const int kv_hi = len - nq + tq_last + 1;
+    const int n_tiles = max(0, (kv_hi + P3_BN - 1) / P3_BN);
+    const int plane_k = ((env * p.n_layer + p.layer) * 2 + 0) * p.n_kv_head + kvh;
+    const int plane_v = plane_k + p.n_kv_head;
+
+    if (tid == 0) {
+        for (int i = 0; i < 12; ++i) mbar_init(BAR(i), 1);
+        mbar_init(BAR(B3_S_FULL), 1); mbar_init(BAR(B3_S_FULL + 1), 1);
+        mbar_init(BAR(B3_P_FULL), PW_SOFTMAX_WARPS); mbar_init(BAR(B3_P_FULL + 1), PW_SOFTMAX_WARPS);
+        mbar_init(BAR(B3_PV_DONE), 1); mbar_init(BAR(B3_PV_DONE + 1), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(s2u(tmem_ptr_smem)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+    const uint32_t TM_S0 = tmem_base, TM_O = tmem_base + 256, TM_Q = tmem_base + 384;
+
+    // Q tile -> TMEM (A operand): warps of quarters 0 and 1 store dims [64*quarter, +64) of their 32 rows
+    if (warp < 8) {
+        const int r = (warp & 3) * 32 + lane, half = warp >> 2;
+        const int R = row0 + r;
+        uint32_t qv[32];
+        if (r < rows_here) {
+            const int tq = R / g, hg = R - tq * g;
+            const int4* src = reinterpret_cast<const int4*>(p.q + ((int64_t)(qs + tq) * p.n_q_head + kvh * g + hg) * P3_HD) + half * 8;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const int4 v = __ldg(src + c);
+                qv[c * 4 + 0] = v.x; qv[c * 4 + 1] = v.y; qv[c * 4 + 2] = v.z; qv[c * 4 + 3] = v.w;
+            }
+        } else {
+#pragma unroll
+            for (int c = 0; c < 32; ++c) qv[c] = 0u;
+        }
+        tmem_st32(TM_Q + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(half * 32), qv);
+        tmem_wait_st();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+
+    if (warp == PW_SOFTMAX_WARPS + 1) {
+        // ------------------------------------------------------------ TMA producer
+        if (elect_one()) asm volatile("prefetch.tensormap [%0];" ::"l"(&kv_map) : "memory");
+        for (int j = 0; j < n_tiles; ++j) {
+            const int st = j % P3_STAGES, u = j / P3_STAGES;
+            const int key0 = j * P3_BN;
+            mbar_wait(BAR(B3_K_EMPTY + st), (u & 1) ^ 1);
+            if (elect_one()) {
+                mbar_expect_tx(BAR(B3_K_FULL + st), P3_TILE);
+                tma_load_3d(sbase + S3_K + st * P3_TILE, &kv_map, BAR(B3_K_FULL + st), 0, key0, plane_k);
+                tma_load_3d(sbase + S3_K + st * P3_TILE + P3_PANEL, &kv_map, BAR(B3_K_FULL + st), 64, key0, plane_k);
+            }
+            mbar_wait(BAR(B3_V_EMPTY + st), (u & 1) ^ 1);
+            if (elect_one()) {
+                mbar_expect_tx(BAR(B3_V_FULL + st), P3_TILE);
+                tma_load_3d(sbase + S3_V + st * P3_TILE, &kv_map, BAR(B3_V_FULL + st), 0, key0, plane_v);
+                tma_load_3d(sbase + S3_V + st * P3_TILE + P3_PANEL, &kv_map, BAR(B3_V_FULL + st), 64, key0, plane_v);
+            }
+            __syncwarp();
+        }
+    } else if (warp == PW_SOFTMAX_WARPS) {
+        // ------------------------------------------------------------ MMA issuer (uniform warp, elected lane)
+        constexpr uint32_t IDESC_QK = umma_idesc(0, 128);
+        constexpr uint32_t IDESC_PV = umma_idesc(1, 128);
+        auto issue_qk = [&](int j) {
+            const int st = j % P3_STAGES, bf = j & 1;
+            mbar_wait(BAR(B3_K_FULL + st), (j / P3_STAGES) & 1);
+            tc_fence_after();
+            const uint32_t kb = sbase + S3_K + st * P3_TILE;
+            if (elect_one()) {
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks)
+                    tc_mma_ts(TM_S0 + bf * 128, TM_Q + ks * 8, umma_desc(kb + (ks >> 2) * P3_PANEL + (ks & 3) * 32, 16, 1024),
+                              IDESC_QK, ks > 0);
+                tc_commit(BAR(B3_S_FULL + bf));
+                tc_commit(BAR(B3_K_EMPTY + st));
+            }
+            __syncwarp();
+        };
+        if (n_tiles > 0) issue_qk(0);
+        for (int j = 0; j < n_tiles; ++j) {
+            if (j + 1 < n_tiles) issue_qk(j + 1);
+            const int st = j % P3_STAGES, bf = j & 1, ub = j >> 1;
+            mbar_wait(BAR(B3_P_FULL + bf), ub & 1);
+            mbar_wait(BAR(B3_V_FULL + st), (j / P3_STAGES) & 1);
+            tc_fence_after();
+            const uint32_t vb = sbase + S3_V + st * P3_TILE;
+            if (elect_one()) {
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks)
+                    tc_mma_ts(TM_O, TM_S0 + bf * 128 + ks * 8, umma_desc(vb + ks * 2048, P3_PANEL, 1024), IDESC_PV,
+                              (j > 0 || ks > 0));
+                tc_commit(BAR(B3_V_EMPTY + st));
+                tc_commit(BAR(B3_PV_DONE + bf));
+            }
+            __syncwarp();
+        }
+    } else {
+        // ------------------------------------------------------------ softmax warps: quadrant qd, score quarter qt
+        const int qd = warp & 3, qt = warp >> 2;
+        const int r = qd * 32 + lane;
+        const int R = row0 + r;
+        const bool row_valid = r < rows_here;
+        const int tq = row_valid ? R / g : 0;
+        const int hg = row_valid ? R - tq * g : 0;
+        const int lim = row_valid ? len - nq + tq + 1 : 0;
+        const uint32_t lane_base = (uint32_t)(qd * 32) << 16;
+        const uint32_t xch = sbase + SW_XCH, xch2 = sbase + SW_XCH2;
+        const int quad_bar = 1 + qd;
+        float m_used = -INFINITY, l_sum = 0.f;
+        for (int j = 0; j < n_tiles; ++j) {
+            const int bf = j & 1, ub = j >> 1;
+            mbar_wait(BAR(B3_S_FULL + bf), ub & 1);
+            tc_fence_after();
+            uint32_t sv[32];
+            tmem_ld32(TM_S0 + bf * 128 + lane_base + qt * 32, sv);
+            tmem_wait_ld();
+            const int key0 = j * P3_BN + qt * 32;
+            float mx = -INFINITY;
+            if (key0 + 32 > lim) {
+#pragma unroll
+                for (int e = 0; e < 32; ++e) {
+                    if (key0 + e >= lim) sv[e] = 0xFF800000u;
+                    mx = fmaxf(mx, __uint_as_float(sv[e]));
+                }
+            } else {
+#pragma unroll
+                for (int e = 0; e < 32; ++e) mx = fmaxf(mx, __uint_as_float(sv[e]));
+            }
+            sts32f(xch + ((bf * 4 + qt) * 128 + r) * 4, mx);
+            // quadrant barrier: (a) row max exchange, (b) all four warps hold their S(j) in registers, so P(j) may
+            // now overwrite columns [0,64) of this S buffer
+            asm volatile("bar.sync %0, 128;" ::"r"(quad_bar) : "memory");
+#pragma unroll
+            for (int o = 1; o < 4; ++o) mx = fmaxf(mx, lds32f(xch + ((bf * 4 + ((qt + o) & 3)) * 128 + r) * 4));
+            mx *= p.scale_log2;
+            float alpha = 1.f;
+            bool rescale = false;
+            if (mx > m_used + 8.0f || (m_used == -INFINITY && mx != -INFINITY)) {   // lazy rescale (factor 2^8)
+                alpha = m_used == -INFINITY ? 0.f : exp2f(m_used - mx);
+                m_used = mx;
+                rescale = j > 0;
+            }
+            const float neg_m = m_used == -INFINITY ? 0.f : -m_used;
+            l_sum *= alpha;
+            if (__any_sync(0xffffffffu, rescale)) {
+                mbar_wait(BAR(B3_PV_DONE + (bf ^ 1)), ((j - 1) >> 1) & 1);   // O quiescent: PV(j-1) done
+                tc_fence_after();
+                uint32_t ov[32];
+                tmem_ld32(TM_O + lane_base + qt * 32, ov);
+                tmem_wait_ld();
+#pragma unroll
+                for (int e = 0; e < 32; ++e) ov[e] = __float_as_uint(__uint_as_float(ov[e]) * alpha);
+                tmem_st32(TM_O + lane_base + qt * 32, ov);
+            }
+            uint32_t pv[16];
+            float psum = 0.f;
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+                const float p0 = ex2_approx(fmaf(__uint_as_float(sv[2 * e]), p.scale_log2, neg_m));
+                const float p1 = ex2_approx(fmaf(__uint_as_float(sv[2 * e + 1]), p.scale_log2, neg_m));
+                psum += p0 + p1;
+                pv[e] = pack2_bf16(p0, p1);
+            }
+            l_sum += psum;
+            tmem_st16(TM_S0 + bf * 128 + lane_base + qt * 16, pv);
+            tmem_wait_st();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(BAR(B3_P_FULL + bf));
+        }
+        // epilogue
+        sts32f(xch2 + (qt * 128 + r) * 4, l_sum);
+        asm volatile("bar.sync %0, 128;" ::"r"(quad_bar) : "memory");
+        float l_tot = 0.f;
+#pragma unroll
+        for (int o = 0; o < 4; ++o) l_tot += lds32f(xch2 + (o * 128 + r) * 4);
+        if (n_tiles > 0) {
+            mbar_wait(BAR(B3_PV_DONE + ((n_tiles - 1) & 1)), ((n_tiles - 1) >> 1) & 1);
+            tc_fence_after();
+        }
+        const float inv_l = l_tot > 0.f ? 1.0f / l_tot : 0.f;
+        __nv_bfloat16* orow = p.out + ((int64_t)(qs + tq) * p.n_q_head + kvh * g + hg) * P3_HD + qt * 32;
+        uint32_t ov[32];
+        tmem_ld32(TM_O + lane_base + qt * 32, ov);
+        tmem_wait_ld();
+        if (row_valid) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                uint32_t w[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    w[e] = pack2_bf16(__uint_as_float(ov[q * 8 + 2 * e]) * inv_l, __uint_as_float(ov[q * 8 + 2 * e + 1]) * inv_l);
+                *reinterpret_cast<int4*>(orow + q * 8) = make_int4(w[0], w[1], w[2], w[3]);
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
     if (warp == 0) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
@@ -462,6 +738,7 @@ int prefill3_launch(const svln_kv_arena* arena, int layer, const void* q, int n_
     if (!attr_set) {
         SVLN_CUDA(cudaFuncSetAttribute(attn_prefill3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, P3_SMEM));
         SVLN_CUDA(cudaFuncSetAttribute(attn_prefill3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, P3_SMEM));
+        SVLN_CUDA(cudaFuncSetAttribute(attn_prefill3w_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PW_SMEM));
         attr_set = true;
     }
     // measured on B200: the multicast pair is ~5 % SLOWER than the plain kernel at the 64-stream shapes (L2 already
@@ -525,7 +802,10 @@ int prefill3_launch(const svln_kv_arena* arena, int layer, const void* q, int n_
         p.part_o = (float*)workspace;
         p.part_ml = p.part_o + (size_t)ctas * n_splits * P3_BM * P3_HD;
         dim3 grid(tiles, arena->n_kv_head, n_splits);
-        if (use_cluster) {
+        static const int wide = getenv("SVLN_PF_WIDE") ? atoi(getenv("SVLN_PF_WIDE")) : 0;
+        if (wide && !use_cluster && n_splits == 1) {
+            attn_prefill3w_kernel<<<grid, PW_THREADS, PW_SMEM, (cudaStream_t)stream>>>(map, p);
+        } else if (use_cluster) {
             cudaLaunchConfig_t cfg = {};
             cfg.gridDim = grid;
             cfg.blockDim = dim3(P3_THREADS);
