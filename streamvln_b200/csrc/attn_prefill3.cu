@@ -83,6 +83,18 @@ struct Prefill3Params {
 #define P3_LIFE(slot_) do { } while (0)
 #endif
 
+// sequence that owns global M tile `gtile`: last b with tile_start[b] <= gtile.  Binary search: the linear scan was a
+// chain of up to 64 dependent constant-bank loads at the very start of every CTA (~1 us of the prologue).
+__device__ __forceinline__ int p3_find_seq(const Prefill3Params& p, int gtile) {
+    int lo = 0, hi = p.n_seq - 1;
+#pragma unroll 1
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (p.tile_start[mid] <= gtile) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
 // D[tmem] (+)= A[tmem] * B[smem]
 __device__ __forceinline__ void tc_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accum) {
     asm volatile(
@@ -126,8 +138,7 @@ attn_prefill3_kernel(const __grid_constant__ CUtensorMap kv_map, const __grid_co
     const int kvh = blockIdx.y;
     const int g = p.n_q_head / p.n_kv_head;
     const int gtile = (int)gridDim.x - 1 - (int)blockIdx.x;   // heaviest (latest rows) first
-    int b = 0;
-    while (b + 1 < p.n_seq && gtile >= p.tile_start[b + 1]) ++b;
+    const int b = p3_find_seq(p, gtile);
     const int mtile = gtile - p.tile_start[b];
     const bool dev = p.d_env != nullptr;
     const int nq = dev ? p.d_n_q[b] : p.n_q[b];
@@ -156,7 +167,8 @@ attn_prefill3_kernel(const __grid_constant__ CUtensorMap kv_map, const __grid_co
     // Prologue, overlapped: the Q rows are requested first (registers only), then barriers and tensor memory are set
     // up while they fly; after the one CTA barrier the TMA warp starts streaming K/V at once, the softmax warps move
     // Q into TMEM and signal Q_FULL, and only the MMA warp waits for it.  (Measured before: 4.1 us from CTA entry to
-    // "Q stored" with these steps in sequence, of the 8.4 us a CTA spends outside its key loop.)
+    // "Q stored" with these steps in sequence, of the 8.4 us a CTA spends outside its key loop; tcgen05.alloc itself
+    // is 666 cycles.  Requesting the first K/V tiles before the CTA barrier as well changed nothing.)
     uint32_t qv[32];
     if (warp < P3_SOFTMAX_WARPS) {
         const int r = (warp & 3) * 32 + lane, half = warp >> 2;
@@ -463,8 +475,7 @@ attn_prefill3w_kernel(const __grid_constant__ CUtensorMap kv_map, const __grid_c
     const int kvh = blockIdx.y;
     const int g = p.n_q_head / p.n_kv_head;
     const int gtile = (int)gridDim.x - 1 - (int)blockIdx.x;   // heaviest (latest rows) first
-    int b = 0;
-    while (b + 1 < p.n_seq && gtile >= p.tile_start[b + 1]) ++b;
+    const int b = p3_find_seq(p, gtile);
     const int mtile = gtile - p.tile_start[b];
     const bool dev = p.d_env != nullptr;
     const int nq = dev ? p.d_n_q[b] : p.n_q[b];
@@ -691,8 +702,7 @@ __global__ void __launch_bounds__(256)
 attn_prefill3_combine_kernel(const __grid_constant__ Prefill3Params p) {
     const int gtile = blockIdx.x, kvh = blockIdx.y;
     const int g = p.n_q_head / p.n_kv_head;
-    int b = 0;
-    while (b + 1 < p.n_seq && gtile >= p.tile_start[b + 1]) ++b;
+    const int b = p3_find_seq(p, gtile);
     const int mtile = gtile - p.tile_start[b];
     const bool dev = p.d_env != nullptr;
     const int nq = dev ? p.d_n_q[b] : p.n_q[b];
