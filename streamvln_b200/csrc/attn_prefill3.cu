@@ -319,6 +319,14 @@ attn_prefill3_kernel(const __grid_constant__ CUtensorMap kv_map, const __grid_co
             mbar_wait(BAR(B3_S_FULL + bf), ub & 1);
             if (trole < 2) P3_TRACE(trole, j, 1);
             tc_fence_after();
+#ifdef SVLN_PF_INSTRUMENT
+            if (p.debug & 2) {   // experiment: no softmax at all (wrong results) - the pure MMA + TMA pipeline rate
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(BAR(B3_P_FULL + bf));
+                continue;
+            }
+#endif
             uint32_t sv[2][32];
             const uint32_t sbuf = TM_S0 + bf * 128 + lane_base;
             tmem_ld32(sbuf + half * 64, sv[0]);
