@@ -457,56 +457,75 @@ attn_prefill3_kernel(const __grid_constant__ CUtensorMap kv_map, const __grid_co
     }
 }
 
-// ---- wide variant: 16 softmax warps -----------------------------------------------------------------------------
-// Measured on the kernel above: time = 0.97 us x key tiles + 8.4 us per CTA, and a persistent version (one CTA per SM
-// walking a list of items, K/V streaming across items) kept the same 7.6 us per ITEM - the fixed cost is pipeline
-// fill/drain, not CTA launch - and 1.0 us (1900 cycles) per tile against 1024 cycles of MMA work: the eight softmax
-// warps are the critical path (64 scores per thread per tile: TMEM load, max, exchange, exp2, pack, TMEM store).
-// Here four warps share each TMEM lane quadrant and take 32 score columns each, so a thread handles 32 scores per
-// tile; the row max / row sum are exchanged among the four through shared memory and one 128-thread named barrier.
-constexpr int PW_SOFTMAX_WARPS = 16;
-constexpr int PW_THREADS = (PW_SOFTMAX_WARPS + 2) * 32;
-constexpr int SW_XCH = S3_BAR + 256;                      // float [2][4][128] row-max exchange
-constexpr int SW_XCH2 = SW_XCH + 2 * 4 * 128 * 4;         // float [4][128] row-sum exchange
-constexpr int PW_SMEM = SW_XCH2 + 4 * 128 * 4;
+// ---- persistent variant ---------------------------------------------------------------------------------------
+// The kernel above costs 0.97 us per key tile plus a fixed ~6.3 us per CTA (launch gap, setup, pipeline fill, O
+// read-out): a fifth of the steady-turn shape (24 key tiles per CTA) and half of the window-start shape (7.5 on
+// average).  Here one CTA per SM walks a list of (M tile, kv head) items and the tensor pipe never drains between
+// them: the TMA warp streams the next item's K/V tiles as ring slots free up; Q is double-buffered in tensor memory
+// (the 64 spare columns), stored one item AHEAD by the softmax warps, so the MMA warp issues the next item's first
+// QK right after the current item's last one - before the current item's last softmax, PV and O read-out - and
+// keeps one global tile counter, so the S/P double buffer and the ring phases simply continue.  What orders the
+// items: Q_FULL[2] (count = softmax warps); O of item i is read out by the softmax warps before they produce
+// P(0) of item i+1, which PV(0) of item i+1 (the first write to O) waits for.
+// MEASURED: not a win - 845 vs 964 TFLOP/s for the plain kernel at 64 x 256 over 3072 keys (1.09 us per tile and
+// still 7.5 us per item), so it is opt-in (SVLN_PF_PERSIST) and kept for the next round's work on the item
+// boundary.  (A first persistent version without the Q double buffer cost 7.6 us per item; a 16-softmax-warp
+// version, 32 scores per thread, did not change the 0.97 us per tile: with the softmax removed the MMA + TMA
+// pipeline alone needs 0.79 us per tile.)
+constexpr int B3P_Q_FULL = B3_COUNT;          // [2], count = softmax warps, one phase per use
+constexpr int B3P_COUNT = B3_COUNT + 2;
+constexpr int S3P_XCH2 = P3_SMEM;             // float [2][128] row-sum exchange of the read-out (separate from the row-max one)
+constexpr int P3P_SMEM = S3P_XCH2 + 2 * 128 * 4;
 
-__global__ void __launch_bounds__(PW_THREADS, 1)
-attn_prefill3w_kernel(const __grid_constant__ CUtensorMap kv_map, const __grid_constant__ Prefill3Params p) {
+struct P3Item {
+    int kvh, nq, len, qs, row0, rows_here, n_tiles, plane_k, plane_v;
+};
+__device__ __forceinline__ P3Item p3_item(const Prefill3Params& p, int it, int total_tiles) {
+    P3Item I;
+    const int gt = total_tiles - 1 - it / p.n_kv_head;     // heaviest (latest rows) first
+    I.kvh = it % p.n_kv_head;
+    const int b = p3_find_seq(p, gt);
+    const int mtile = gt - p.tile_start[b];
+    const bool dev = p.d_env != nullptr;
+    I.nq = dev ? p.d_n_q[b] : p.n_q[b];
+    I.len = dev ? p.d_kv_len[b] : p.kv_len[b];
+    const int env = dev ? p.d_env[b] : p.env[b];
+    I.qs = dev ? p.d_q_start[b] : p.q_start[b];
+    const int g = p.n_q_head / p.n_kv_head;
+    const int rows_total = I.nq * g;
+    I.row0 = mtile * P3_BM;
+    I.rows_here = min(P3_BM, rows_total - I.row0);
+    const int tq_last = (I.row0 + I.rows_here - 1) / g;
+    const int kv_hi = I.len - I.nq + tq_last + 1;
+    I.n_tiles = max(0, (kv_hi + P3_BN - 1) / P3_BN);
+    I.plane_k = ((env * p.n_layer + p.layer) * 2 + 0) * p.n_kv_head + I.kvh;
+    I.plane_v = I.plane_k + p.n_kv_head;
+    return I;
+}
+
+__global__ void __launch_bounds__(P3_THREADS, 1)
+attn_prefill3p_kernel(const __grid_constant__ CUtensorMap kv_map, const __grid_constant__ Prefill3Params p) {
     extern __shared__ __align__(1024) unsigned char smem[];
     const uint32_t sbase = s2u(smem);
     if ((sbase & 1023u) != 0) __trap();
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + S3_BAR + B3_COUNT * 8);
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + S3_BAR + B3P_COUNT * 8);
     const uint32_t bar0 = sbase + S3_BAR;
     auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
-
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int kvh = blockIdx.y;
     const int g = p.n_q_head / p.n_kv_head;
-    const int gtile = (int)gridDim.x - 1 - (int)blockIdx.x;   // heaviest (latest rows) first
-    const int b = p3_find_seq(p, gtile);
-    const int mtile = gtile - p.tile_start[b];
-    const bool dev = p.d_env != nullptr;
-    const int nq = dev ? p.d_n_q[b] : p.n_q[b];
-    const int len = dev ? p.d_kv_len[b] : p.kv_len[b];
-    const int env = dev ? p.d_env[b] : p.env[b];
-    const int qs = dev ? p.d_q_start[b] : p.q_start[b];
-    const int rows_total = nq * g;
-    const int row0 = mtile * P3_BM;
-    const int rows_here = min(P3_BM, rows_total - row0);
-    const int tq_last = (row0 + rows_here - 1) / g;
-    const int kv_hi = len - nq + tq_last + 1;
-    const int n_tiles = max(0, (kv_hi + P3_BN - 1) / P3_BN);
-    const int plane_k = ((env * p.n_layer + p.layer) * 2 + 0) * p.n_kv_head + kvh;
-    const int plane_v = plane_k + p.n_kv_head;
+    const int total_tiles = p.tile_start[P3_MAX_SEQ];
+    const int n_items = total_tiles * p.n_kv_head;
+    const int stride = gridDim.x;
 
     if (tid == 0) {
         for (int i = 0; i < 12; ++i) mbar_init(BAR(i), 1);
         mbar_init(BAR(B3_S_FULL), 1); mbar_init(BAR(B3_S_FULL + 1), 1);
-        mbar_init(BAR(B3_P_FULL), PW_SOFTMAX_WARPS); mbar_init(BAR(B3_P_FULL + 1), PW_SOFTMAX_WARPS);
+        mbar_init(BAR(B3_P_FULL), P3_SOFTMAX_WARPS); mbar_init(BAR(B3_P_FULL + 1), P3_SOFTMAX_WARPS);
         mbar_init(BAR(B3_PV_DONE), 1); mbar_init(BAR(B3_PV_DONE + 1), 1);
+        mbar_init(BAR(B3P_Q_FULL), P3_SOFTMAX_WARPS); mbar_init(BAR(B3P_Q_FULL + 1), P3_SOFTMAX_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 0) {
+    if (warp == P3_SOFTMAX_WARPS) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(s2u(tmem_ptr_smem)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -514,192 +533,260 @@ attn_prefill3w_kernel(const __grid_constant__ CUtensorMap kv_map, const __grid_c
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
-    const uint32_t TM_S0 = tmem_base, TM_O = tmem_base + 256, TM_Q = tmem_base + 384;
+    const uint32_t TM_S0 = tmem_base, TM_O = tmem_base + 256, TM_Q = tmem_base + 384;   // Q buffers at +384 and +448
 
-    // Q tile -> TMEM (A operand): warps of quarters 0 and 1 store dims [64*quarter, +64) of their 32 rows
-    if (warp < 8) {
-        const int r = (warp & 3) * 32 + lane, half = warp >> 2;
-        const int R = row0 + r;
-        uint32_t qv[32];
-        if (r < rows_here) {
-            const int tq = R / g, hg = R - tq * g;
-            const int4* src = reinterpret_cast<const int4*>(p.q + ((int64_t)(qs + tq) * p.n_q_head + kvh * g + hg) * P3_HD) + half * 8;
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                const int4 v = __ldg(src + c);
-                qv[c * 4 + 0] = v.x; qv[c * 4 + 1] = v.y; qv[c * 4 + 2] = v.z; qv[c * 4 + 3] = v.w;
-            }
-        } else {
-#pragma unroll
-            for (int c = 0; c < 32; ++c) qv[c] = 0u;
-        }
-        tmem_st32(TM_Q + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(half * 32), qv);
-        tmem_wait_st();
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-
-    if (warp == PW_SOFTMAX_WARPS + 1) {
-        // ------------------------------------------------------------ TMA producer
+    if (warp == P3_SOFTMAX_WARPS + 1) {
+        // ------------------------------------------------------------ TMA producer: runs ahead across items
         if (elect_one()) asm volatile("prefetch.tensormap [%0];" ::"l"(&kv_map) : "memory");
-        for (int j = 0; j < n_tiles; ++j) {
-            const int st = j % P3_STAGES, u = j / P3_STAGES;
-            const int key0 = j * P3_BN;
-            mbar_wait(BAR(B3_K_EMPTY + st), (u & 1) ^ 1);
-            if (elect_one()) {
-                mbar_expect_tx(BAR(B3_K_FULL + st), P3_TILE);
-                tma_load_3d(sbase + S3_K + st * P3_TILE, &kv_map, BAR(B3_K_FULL + st), 0, key0, plane_k);
-                tma_load_3d(sbase + S3_K + st * P3_TILE + P3_PANEL, &kv_map, BAR(B3_K_FULL + st), 64, key0, plane_k);
+        uint32_t T = 0;
+        for (int it = blockIdx.x; it < n_items; it += stride) {
+            const P3Item I = p3_item(p, it, total_tiles);
+            for (int j = 0; j < I.n_tiles; ++j, ++T) {
+                const int st = T % P3_STAGES;
+                const uint32_t u = T / P3_STAGES;
+                const int key0 = j * P3_BN;
+                mbar_wait(BAR(B3_K_EMPTY + st), (u & 1) ^ 1);
+                if (elect_one()) {
+                    mbar_expect_tx(BAR(B3_K_FULL + st), P3_TILE);
+                    tma_load_3d(sbase + S3_K + st * P3_TILE, &kv_map, BAR(B3_K_FULL + st), 0, key0, I.plane_k);
+                    tma_load_3d(sbase + S3_K + st * P3_TILE + P3_PANEL, &kv_map, BAR(B3_K_FULL + st), 64, key0, I.plane_k);
+                }
+                mbar_wait(BAR(B3_V_EMPTY + st), (u & 1) ^ 1);
+                if (elect_one()) {
+                    mbar_expect_tx(BAR(B3_V_FULL + st), P3_TILE);
+                    tma_load_3d(sbase + S3_V + st * P3_TILE, &kv_map, BAR(B3_V_FULL + st), 0, key0, I.plane_v);
+                    tma_load_3d(sbase + S3_V + st * P3_TILE + P3_PANEL, &kv_map, BAR(B3_V_FULL + st), 64, key0, I.plane_v);
+                }
+                __syncwarp();
             }
-            mbar_wait(BAR(B3_V_EMPTY + st), (u & 1) ^ 1);
-            if (elect_one()) {
-                mbar_expect_tx(BAR(B3_V_FULL + st), P3_TILE);
-                tma_load_3d(sbase + S3_V + st * P3_TILE, &kv_map, BAR(B3_V_FULL + st), 0, key0, plane_v);
-                tma_load_3d(sbase + S3_V + st * P3_TILE + P3_PANEL, &kv_map, BAR(B3_V_FULL + st), 64, key0, plane_v);
-            }
-            __syncwarp();
         }
-    } else if (warp == PW_SOFTMAX_WARPS) {
+    } else if (warp == P3_SOFTMAX_WARPS) {
         // ------------------------------------------------------------ MMA issuer (uniform warp, elected lane)
         constexpr uint32_t IDESC_QK = umma_idesc(0, 128);
         constexpr uint32_t IDESC_PV = umma_idesc(1, 128);
-        auto issue_qk = [&](int j) {
-            const int st = j % P3_STAGES, bf = j & 1;
-            mbar_wait(BAR(B3_K_FULL + st), (j / P3_STAGES) & 1);
+        auto issue_qk = [&](uint32_t T, uint32_t qbuf) {
+            const int st = T % P3_STAGES, bf = T & 1;
+            mbar_wait(BAR(B3_K_FULL + st), (T / P3_STAGES) & 1);
             tc_fence_after();
             const uint32_t kb = sbase + S3_K + st * P3_TILE;
             if (elect_one()) {
 #pragma unroll
                 for (int ks = 0; ks < 8; ++ks)
-                    tc_mma_ts(TM_S0 + bf * 128, TM_Q + ks * 8, umma_desc(kb + (ks >> 2) * P3_PANEL + (ks & 3) * 32, 16, 1024),
-                              IDESC_QK, ks > 0);
+                    tc_mma_ts(TM_S0 + bf * 128, TM_Q + qbuf * 64 + ks * 8,
+                              umma_desc(kb + (ks >> 2) * P3_PANEL + (ks & 3) * 32, 16, 1024), IDESC_QK, ks > 0);
                 tc_commit(BAR(B3_S_FULL + bf));
                 tc_commit(BAR(B3_K_EMPTY + st));
             }
             __syncwarp();
         };
-        if (n_tiles > 0) issue_qk(0);
-        for (int j = 0; j < n_tiles; ++j) {
-            if (j + 1 < n_tiles) issue_qk(j + 1);
-            const int st = j % P3_STAGES, bf = j & 1, ub = j >> 1;
-            mbar_wait(BAR(B3_P_FULL + bf), ub & 1);
-            mbar_wait(BAR(B3_V_FULL + st), (j / P3_STAGES) & 1);
+        // first QK of item `idx` (its tile counter starts at T): its Q must be in tensor memory
+        auto first_qk = [&](uint32_t idx, uint32_t T) {
+            mbar_wait(BAR(B3P_Q_FULL + (idx & 1)), (idx >> 1) & 1);
             tc_fence_after();
-            const uint32_t vb = sbase + S3_V + st * P3_TILE;
-            if (elect_one()) {
+            issue_qk(T, idx & 1);
+        };
+        uint32_t T0 = 0, idx = 0;
+        bool first_issued = false;
+        for (int it = blockIdx.x; it < n_items; it += stride, ++idx) {
+            const P3Item I = p3_item(p, it, total_tiles);
+            const int it_next = it + stride;
+            int next_tiles = 0;
+            if (it_next < n_items) next_tiles = p3_item(p, it_next, total_tiles).n_tiles;
+            if (I.n_tiles > 0 && !first_issued) first_qk(idx, T0);
+            first_issued = false;
+            for (int j = 0; j < I.n_tiles; ++j) {
+                const uint32_t T = T0 + j;
+                if (j + 1 < I.n_tiles) {
+                    issue_qk(T + 1, idx & 1);
+                } else if (next_tiles > 0) {      // keep the tensor pipe fed across the item boundary
+                    first_qk(idx + 1, T + 1);
+                    first_issued = true;
+                }
+                const int st = T % P3_STAGES, bf = T & 1;
+                mbar_wait(BAR(B3_P_FULL + bf), (T >> 1) & 1);
+                mbar_wait(BAR(B3_V_FULL + st), (T / P3_STAGES) & 1);
+                tc_fence_after();
+                const uint32_t vb = sbase + S3_V + st * P3_TILE;
+                if (elect_one()) {
 #pragma unroll
-                for (int ks = 0; ks < 8; ++ks)
-                    tc_mma_ts(TM_O, TM_S0 + bf * 128 + ks * 8, umma_desc(vb + ks * 2048, P3_PANEL, 1024), IDESC_PV,
-                              (j > 0 || ks > 0));
-                tc_commit(BAR(B3_V_EMPTY + st));
-                tc_commit(BAR(B3_PV_DONE + bf));
+                    for (int ks = 0; ks < 8; ++ks)
+                        tc_mma_ts(TM_O, TM_S0 + bf * 128 + ks * 8, umma_desc(vb + ks * 2048, P3_PANEL, 1024), IDESC_PV,
+                                  (j > 0 || ks > 0));
+                    tc_commit(BAR(B3_V_EMPTY + st));
+                    tc_commit(BAR(B3_PV_DONE + bf));
+                }
+                __syncwarp();
             }
-            __syncwarp();
+            T0 += I.n_tiles;
         }
     } else {
-        // ------------------------------------------------------------ softmax warps: quadrant qd, score quarter qt
-        const int qd = warp & 3, qt = warp >> 2;
-        const int r = qd * 32 + lane;
-        const int R = row0 + r;
-        const bool row_valid = r < rows_here;
-        const int tq = row_valid ? R / g : 0;
-        const int hg = row_valid ? R - tq * g : 0;
-        const int lim = row_valid ? len - nq + tq + 1 : 0;
-        const uint32_t lane_base = (uint32_t)(qd * 32) << 16;
-        const uint32_t xch = sbase + SW_XCH, xch2 = sbase + SW_XCH2;
-        const int quad_bar = 1 + qd;
-        float m_used = -INFINITY, l_sum = 0.f;
-        for (int j = 0; j < n_tiles; ++j) {
-            const int bf = j & 1, ub = j >> 1;
-            mbar_wait(BAR(B3_S_FULL + bf), ub & 1);
-            tc_fence_after();
-            uint32_t sv[32];
-            tmem_ld32(TM_S0 + bf * 128 + lane_base + qt * 32, sv);
-            tmem_wait_ld();
-            const int key0 = j * P3_BN + qt * 32;
-            float mx = -INFINITY;
-            if (key0 + 32 > lim) {
+        // ------------------------------------------------------------ softmax warps
+        const int r = (warp & 3) * 32 + lane;
+        const int half = warp >> 2;
+        const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+        const uint32_t xch = sbase + S3_XCH, xch2 = sbase + S3P_XCH2;
+        const int pair_bar = 1 + (warp & 3);
+        auto load_q = [&](const P3Item& I, uint32_t (&qv)[32]) {
+            const int R = I.row0 + r;
+            if (r < I.rows_here) {
+                const int tq = R / g, hg = R - tq * g;
+                const int4* src = reinterpret_cast<const int4*>(p.q + ((int64_t)(I.qs + tq) * p.n_q_head + I.kvh * g + hg) * P3_HD) + half * 8;
 #pragma unroll
-                for (int e = 0; e < 32; ++e) {
-                    if (key0 + e >= lim) sv[e] = 0xFF800000u;
-                    mx = fmaxf(mx, __uint_as_float(sv[e]));
+                for (int c = 0; c < 8; ++c) {
+                    const int4 v = __ldg(src + c);
+                    qv[c * 4 + 0] = v.x; qv[c * 4 + 1] = v.y; qv[c * 4 + 2] = v.z; qv[c * 4 + 3] = v.w;
                 }
             } else {
 #pragma unroll
-                for (int e = 0; e < 32; ++e) mx = fmaxf(mx, __uint_as_float(sv[e]));
+                for (int c = 0; c < 32; ++c) qv[c] = 0u;
             }
-            sts32f(xch + ((bf * 4 + qt) * 128 + r) * 4, mx);
-            // quadrant barrier: (a) row max exchange, (b) all four warps hold their S(j) in registers, so P(j) may
-            // now overwrite columns [0,64) of this S buffer
-            asm volatile("bar.sync %0, 128;" ::"r"(quad_bar) : "memory");
-#pragma unroll
-            for (int o = 1; o < 4; ++o) mx = fmaxf(mx, lds32f(xch + ((bf * 4 + ((qt + o) & 3)) * 128 + r) * 4));
-            mx *= p.scale_log2;
-            float alpha = 1.f;
-            bool rescale = false;
-            if (mx > m_used + 8.0f || (m_used == -INFINITY && mx != -INFINITY)) {   // lazy rescale (factor 2^8)
-                alpha = m_used == -INFINITY ? 0.f : exp2f(m_used - mx);
-                m_used = mx;
-                rescale = j > 0;
-            }
-            const float neg_m = m_used == -INFINITY ? 0.f : -m_used;
-            l_sum *= alpha;
-            if (__any_sync(0xffffffffu, rescale)) {
-                mbar_wait(BAR(B3_PV_DONE + (bf ^ 1)), ((j - 1) >> 1) & 1);   // O quiescent: PV(j-1) done
-                tc_fence_after();
-                uint32_t ov[32];
-                tmem_ld32(TM_O + lane_base + qt * 32, ov);
-                tmem_wait_ld();
-#pragma unroll
-                for (int e = 0; e < 32; ++e) ov[e] = __float_as_uint(__uint_as_float(ov[e]) * alpha);
-                tmem_st32(TM_O + lane_base + qt * 32, ov);
-            }
-            uint32_t pv[16];
-            float psum = 0.f;
-#pragma unroll
-            for (int e = 0; e < 16; ++e) {
-                const float p0 = ex2_approx(fmaf(__uint_as_float(sv[2 * e]), p.scale_log2, neg_m));
-                const float p1 = ex2_approx(fmaf(__uint_as_float(sv[2 * e + 1]), p.scale_log2, neg_m));
-                psum += p0 + p1;
-                pv[e] = pack2_bf16(p0, p1);
-            }
-            l_sum += psum;
-            tmem_st16(TM_S0 + bf * 128 + lane_base + qt * 16, pv);
+        };
+        auto store_q = [&](uint32_t idx, const uint32_t (&qv)[32]) {
+            tmem_st32(TM_Q + (idx & 1) * 64 + lane_base + (uint32_t)(half * 32), qv);
             tmem_wait_st();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(BAR(B3_P_FULL + bf));
-        }
-        // epilogue
-        sts32f(xch2 + (qt * 128 + r) * 4, l_sum);
-        asm volatile("bar.sync %0, 128;" ::"r"(quad_bar) : "memory");
-        float l_tot = 0.f;
-#pragma unroll
-        for (int o = 0; o < 4; ++o) l_tot += lds32f(xch2 + (o * 128 + r) * 4);
-        if (n_tiles > 0) {
-            mbar_wait(BAR(B3_PV_DONE + ((n_tiles - 1) & 1)), ((n_tiles - 1) >> 1) & 1);
-            tc_fence_after();
-        }
-        const float inv_l = l_tot > 0.f ? 1.0f / l_tot : 0.f;
-        __nv_bfloat16* orow = p.out + ((int64_t)(qs + tq) * p.n_q_head + kvh * g + hg) * P3_HD + qt * 32;
-        uint32_t ov[32];
-        tmem_ld32(TM_O + lane_base + qt * 32, ov);
-        tmem_wait_ld();
-        if (row_valid) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                uint32_t w[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e)
-                    w[e] = pack2_bf16(__uint_as_float(ov[q * 8 + 2 * e]) * inv_l, __uint_as_float(ov[q * 8 + 2 * e + 1]) * inv_l);
-                *reinterpret_cast<int4*>(orow + q * 8) = make_int4(w[0], w[1], w[2], w[3]);
+            if (lane == 0) mbar_arrive(BAR(B3P_Q_FULL + (idx & 1)));
+        };
+        P3Item I;
+        {
+            uint32_t qv[32];
+            if ((int)blockIdx.x < n_items) {
+                I = p3_item(p, blockIdx.x, total_tiles);
+                load_q(I, qv);
+                store_q(0, qv);
             }
         }
-        tc_fence_before();
+        uint32_t T0 = 0, idx = 0;
+        for (int it = blockIdx.x; it < n_items; it += stride, ++idx) {
+            // the NEXT item's Q rows are requested now and stored into the other Q buffer after this item's first
+            // tile: every QK of item idx-1 (the buffer's previous user) completed before this item started
+            const int it_next = it + stride;
+            const bool has_next = it_next < n_items;
+            P3Item In = I;
+            uint32_t qn[32];
+            if (has_next) {
+                In = p3_item(p, it_next, total_tiles);
+                load_q(In, qn);
+            }
+            bool q_stored = !has_next;
+            const int R = I.row0 + r;
+            const bool row_valid = r < I.rows_here;
+            const int tq = row_valid ? R / g : 0;
+            const int hg = row_valid ? R - tq * g : 0;
+            const int lim = row_valid ? I.len - I.nq + tq + 1 : 0;
+            const int n_tiles = I.n_tiles;
+            float m_used = -INFINITY, l_sum = 0.f;
+            for (int j = 0; j < n_tiles; ++j) {
+                const uint32_t T = T0 + j;
+                const int bf = T & 1;
+                mbar_wait(BAR(B3_S_FULL + bf), (T >> 1) & 1);
+                tc_fence_after();
+                uint32_t sv[2][32];
+                const uint32_t sbuf = TM_S0 + bf * 128 + lane_base;
+                tmem_ld32(sbuf + half * 64, sv[0]);
+                tmem_ld32(sbuf + half * 64 + 32, sv[1]);
+                tmem_wait_ld();
+                const int key0 = j * P3_BN + half * 64;
+                float mx = -INFINITY;
+                if (key0 + 64 > lim) {
+#pragma unroll
+                    for (int c = 0; c < 2; ++c)
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) {
+                            if (key0 + c * 32 + e >= lim) sv[c][e] = 0xFF800000u;
+                            mx = fmaxf(mx, __uint_as_float(sv[c][e]));
+                        }
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 2; ++c)
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) mx = fmaxf(mx, __uint_as_float(sv[c][e]));
+                }
+                sts32f(xch + ((bf * 2 + half) * 128 + r) * 4, mx);
+                asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+                mx = fmaxf(mx, lds32f(xch + ((bf * 2 + (half ^ 1)) * 128 + r) * 4)) * p.scale_log2;
+                float alpha = 1.f;
+                bool rescale = false;
+                if (mx > m_used + 8.0f || (m_used == -INFINITY && mx != -INFINITY)) {   // lazy rescale (factor 2^8)
+                    alpha = m_used == -INFINITY ? 0.f : exp2f(m_used - mx);
+                    m_used = mx;
+                    rescale = j > 0;
+                }
+                const float neg_m = m_used == -INFINITY ? 0.f : -m_used;
+                l_sum *= alpha;
+                if (__any_sync(0xffffffffu, rescale)) {
+                    mbar_wait(BAR(B3_PV_DONE + (bf ^ 1)), ((T - 1) >> 1) & 1);   // O quiescent: PV(T-1) done
+                    tc_fence_after();
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        uint32_t ov[32];
+                        tmem_ld32(TM_O + lane_base + half * 64 + c * 32, ov);
+                        tmem_wait_ld();
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) ov[e] = __float_as_uint(__uint_as_float(ov[e]) * alpha);
+                        tmem_st32(TM_O + lane_base + half * 64 + c * 32, ov);
+                    }
+                }
+                uint32_t pv[32];
+                float psum = 0.f;
+#pragma unroll
+                for (int c = 0; c < 2; ++c)
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) {
+                        const float p0 = ex2_approx(fmaf(__uint_as_float(sv[c][2 * e]), p.scale_log2, neg_m));
+                        const float p1 = ex2_approx(fmaf(__uint_as_float(sv[c][2 * e + 1]), p.scale_log2, neg_m));
+                        psum += p0 + p1;
+                        pv[c * 16 + e] = pack2_bf16(p0, p1);
+                    }
+                l_sum += psum;
+                tmem_st32(TM_S0 + bf * 128 + lane_base + half * 32, pv);
+                tmem_wait_st();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(BAR(B3_P_FULL + bf));
+                if (!q_stored) {   // after the first tile: off the critical path of this item's pipeline fill
+                    store_q(idx + 1, qn);
+                    q_stored = true;
+                }
+            }
+            if (!q_stored) store_q(idx + 1, qn);   // an item without tiles
+            // read-out of this item
+            sts32f(xch2 + (half * 128 + r) * 4, l_sum);
+            asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+            const float l_tot = l_sum + lds32f(xch2 + ((half ^ 1) * 128 + r) * 4);
+            if (n_tiles > 0) {
+                const uint32_t Tl = T0 + n_tiles - 1;
+                mbar_wait(BAR(B3_PV_DONE + (Tl & 1)), (Tl >> 1) & 1);
+                tc_fence_after();
+            }
+            const float inv_l = l_tot > 0.f ? 1.0f / l_tot : 0.f;
+            __nv_bfloat16* orow = p.out + ((int64_t)(I.qs + tq) * p.n_q_head + I.kvh * g + hg) * P3_HD + half * 64;
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                uint32_t ov[32];
+                tmem_ld32(TM_O + lane_base + half * 64 + c * 32, ov);
+                tmem_wait_ld();
+                if (row_valid && n_tiles > 0) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        uint32_t w[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)
+                            w[e] = pack2_bf16(__uint_as_float(ov[q * 8 + 2 * e]) * inv_l, __uint_as_float(ov[q * 8 + 2 * e + 1]) * inv_l);
+                        *reinterpret_cast<int4*>(orow + c * 32 + q * 8) = make_int4(w[0], w[1], w[2], w[3]);
+                    }
+                }
+            }
+            tc_fence_before();
+            // the row-sum slots are reused by the next item's read-out only after both halves have read them
+            asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+            T0 += n_tiles;
+            I = In;
+        }
     }
     __syncthreads();
-    if (warp == 0) {
+    if (warp == P3_SOFTMAX_WARPS) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
     }
@@ -756,7 +843,7 @@ int prefill3_launch(const svln_kv_arena* arena, int layer, const void* q, int n_
     if (!attr_set) {
         SVLN_CUDA(cudaFuncSetAttribute(attn_prefill3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, P3_SMEM));
         SVLN_CUDA(cudaFuncSetAttribute(attn_prefill3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, P3_SMEM));
-        SVLN_CUDA(cudaFuncSetAttribute(attn_prefill3w_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PW_SMEM));
+        SVLN_CUDA(cudaFuncSetAttribute(attn_prefill3p_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P3P_SMEM));
         attr_set = true;
     }
     // measured on B200: the multicast pair is ~5 % SLOWER than the plain kernel at the 64-stream shapes (L2 already
@@ -820,9 +907,12 @@ int prefill3_launch(const svln_kv_arena* arena, int layer, const void* q, int n_
         p.part_o = (float*)workspace;
         p.part_ml = p.part_o + (size_t)ctas * n_splits * P3_BM * P3_HD;
         dim3 grid(tiles, arena->n_kv_head, n_splits);
-        static const int wide = getenv("SVLN_PF_WIDE") ? atoi(getenv("SVLN_PF_WIDE")) : 0;
-        if (wide && !use_cluster && n_splits == 1) {
-            attn_prefill3w_kernel<<<grid, PW_THREADS, PW_SMEM, (cudaStream_t)stream>>>(map, p);
+        // persistent variant: pays off as soon as some SM would run more than one CTA of the plain kernel
+        // (SVLN_PF_PERSIST: 0 never, 1 when the grid exceeds the SM count, 2 always - tests)
+        static const int persist = getenv("SVLN_PF_PERSIST") ? atoi(getenv("SVLN_PF_PERSIST")) : 0;
+        if (persist && !use_cluster && n_splits == 1 && (ctas > sm_count() || persist == 2)) {
+            const int pgrid = ctas < sm_count() ? ctas : sm_count();
+            attn_prefill3p_kernel<<<pgrid, P3_THREADS, P3P_SMEM, (cudaStream_t)stream>>>(map, p);
         } else if (use_cluster) {
             cudaLaunchConfig_t cfg = {};
             cfg.gridDim = grid;

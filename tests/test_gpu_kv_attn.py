@@ -182,6 +182,7 @@ def test_decode_attention(svln_lib, cuda, Hq, Hkv, lens, nqs):
     (28, 4, [1800], [1800]),                   # window start
     (4, 2, [100, 300, 129], [1, 128, 129]),    # ragged batch incl. a single-row chunk
     (8, 8, [640], [77]),
+    (28, 4, [900, 1500, 400], [300, 257, 400]),   # 216 (M tile, kv head) items: more than one per SM, ragged key ranges
 ])
 def test_prefill_attention_tcgen05(svln_lib, cuda, Hq, Hkv, lens, nqs):
     from streamvln_b200.kv_arena import KvArena
@@ -197,6 +198,21 @@ def test_prefill_attention_tcgen05(svln_lib, cuda, Hq, Hkv, lens, nqs):
     ar.attn_prefill(1, q, Hq, list(range(len(lens))), qs, nqs, lens, scale, out)
     torch.cuda.synchronize()
     _check_attn(out, q, ar, 1, [(e, qs[e], nqs[e], lens[e]) for e in range(len(lens))], scale, Hq)
+
+
+@pytest.mark.parametrize("var,val", [("SVLN_PF_PERSIST", "2"), ("SVLN_PF_SPLITS", "3"), ("SVLN_PF_CLUSTER", "1")])
+def test_prefill_attention_opt_in_variants(svln_lib, cuda, var, val):
+    """The measured-but-not-default variants of the prefill kernel (persistent CTAs with a double-buffered Q,
+    split-KV with a combine pass, 2-CTA cluster with multicast K/V) stay correct: the same parity cases in a child
+    process with the switch set (the library reads these switches once)."""
+    import os
+    import subprocess
+    import sys
+
+    env = dict(os.environ, **{var: val})
+    r = subprocess.run([sys.executable, "-m", "pytest", __file__, "-q", "-x", "-m", "gpu", "-k", "test_prefill_attention_tcgen05"],
+                       env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
 
 
 def test_prefill_equals_decode_path(svln_lib, cuda):
