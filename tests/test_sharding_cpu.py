@@ -136,3 +136,31 @@ def test_no_misencoded_ldgsts_in_the_library():
     sass = subprocess.run([cuobjdump, "-sass", str(_lib.LIB_PATH)], capture_output=True, text=True, check=True).stdout
     bad = [l.strip() for l in sass.splitlines() if "LDGSTS" in l and re.search(r"desc\[UR\d*[13579]\]", l)]
     assert not bad, bad[:3]
+
+
+def test_decode_stack_abi_argument_checks():
+    """svln_decode_stack_* validate their descriptor before touching the device (runs without a GPU): one stream only,
+    head_dim 128, matching arena, non-null buffers; errors are negative errno-style codes with a message."""
+    import ctypes as C
+    from streamvln_b200 import _lib
+
+    lib = _lib.load()
+    d = _lib.DecodeStackStruct()
+    d.n_layer, d.hidden, d.inter, d.n_q_head, d.n_kv_head, d.head_dim, d.vocab, d.n_stream = 28, 3584, 18944, 28, 4, 128, 152064, 1
+    assert lib.svln_decode_stack_workspace_bytes(C.byref(d)) > 14 * 3584          # room for the activation vectors
+    d.n_stream = 2
+    assert lib.svln_decode_stack_workspace_bytes(C.byref(d)) == 0                 # single-stream ABI (DESIGN.md section 5)
+    d.n_stream = 1
+    arena = _lib.KvArenaStruct()
+    assert lib.svln_decode_stack_step(C.byref(arena), C.byref(d), None) == -22    # null arena base
+    assert b"svln_decode_stack_step" in lib.svln_last_error()
+    arena.base, arena.n_env, arena.n_layer, arena.n_kv_head, arena.head_dim, arena.max_len = 4096, 1, 28, 4, 128, 4096
+    d.n_stream = 3
+    assert lib.svln_decode_stack_step(C.byref(arena), C.byref(d), None) == -34    # ERANGE: caller falls back
+    d.n_stream, d.head_dim = 1, 64
+    assert lib.svln_decode_stack_step(C.byref(arena), C.byref(d), None) == -22
+    d.head_dim = 128
+    assert lib.svln_decode_stack_step(C.byref(arena), C.byref(d), None) == -22    # null weight / token pointers
+    assert lib.svln_pool_bilinear(None, 1, 27, 14, 3584, None, None) == -22
+    assert lib.svln_pool_bilinear(None, 0, 27, 14, 3584, None, None) == 0         # nothing to do
+    assert lib.svln_pool_bilinear(None, 1, 27, 14, 3583, None, None) == -22       # dim must be a multiple of 8
