@@ -30,7 +30,9 @@
 // fencing after the weight prologue (the fence waits for the copies: +3-6 us per barrier); 512-byte coalesced
 // requests instead of 8 rows x 64 B (35 % slower in DRAM); no L2 evict_first hint on the weight copies (12 % slower);
 // an 8-warp attention item with the O projection's weights streaming behind it (5 % slower); prefetch.global.L2
-// of the attention tiles one phase early (6 % slower: every use of the L2 prefetch instructions cost more than it hid).
+// of the attention tiles one phase early (6 % slower: every use of the L2 prefetch instructions cost more than it hid);
+// a barrier whose last arriver publishes a generation number to eight separate flag lines that the CTAs poll instead
+// of the arrival counter (3-6 % slower: one more L2 round trip per barrier than it saves in poll contention).
 // Rounding points are those of the unfused path (fused_ops.cu, kv_window.cu rope8, gemv.cu), i.e. HF's bf16
 // modules; accumulation order differs from cuBLAS, which the parity tolerance (1e-2 on logits) covers.
 #include <stdlib.h>
