@@ -172,6 +172,7 @@ __device__ __forceinline__ void grid_wait(unsigned* sync, unsigned epoch, int G)
 // so the caller runs it BEFORE waiting for the previous phase (grid barrier) and building x; gemv_finish streams
 // the rest.
 constexpr int MK_RING_SLOTS = 24;                  // 4 KB ring slots (one lane-private int4 per thread each): 96 KB
+                                                   // (measured, time relative to the unfused path: 16 slots 0.98, 24: 0.92-0.95, 32: 1.03)
 constexpr int MK_MAX_SB = 4;
 struct GemvCursor {
     int it, st, sup;                  // next step to issue: flat index, step within the super-block, super-block
