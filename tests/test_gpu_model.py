@@ -314,9 +314,10 @@ def test_gpu_image_processor_matches_pil(svln_lib, cuda):
 
 
 def test_pool_bilinear_kernel_matches_reference_pool(svln_lib, cuda):
-    """svln_pool_bilinear vs the oracle's get_2dPool restatement (CPU F.interpolate, pinned against the reference's own
-    code by tests/golden/ref_glue_*.npz), for the SigLIP grid and the sweep grids.  Floating point: at most one bf16
-    ulp (2^-7 relative) on at most 2e-4 of the elements - ATen's fused-multiply-add pattern is not reproducible."""
+    """svln_pool_bilinear is BIT-EXACT against glue.pool_bilinear_spec (the stated fp32 arithmetic), and within one bf16
+    ulp on at most 2e-4 of the elements of the oracle's get_2dPool restatement (CPU F.interpolate, pinned against the
+    reference's own code by tests/golden/ref_glue_*.npz) - ATen's fused-multiply-add pattern is not reproducible.
+    Shapes: the SigLIP grid and the sweep grids."""
     from streamvln_b200.vision import pool_2d
 
     g = torch.Generator().manual_seed(5)
@@ -325,6 +326,7 @@ def test_pool_bilinear_kernel_matches_reference_pool(svln_lib, cuda):
         want = glue.pool_2d(x, side, 2, "bilinear")                     # bf16 in, fp32 opmath, bf16 out
         got = pool_2d(x.to(cuda), side, 2, "bilinear").cpu()
         assert got.shape == want.shape == (frames, ((side + 1) // 2) ** 2, dim)
+        assert torch.equal(got, glue.pool_bilinear_spec(x, side, 2)), (side, dim)   # bit-exact against the stated arithmetic
         diff = (got.float() - want.float()).abs()
         assert float((diff > 0).float().mean()) <= 2e-4, (side, dim, float((diff > 0).float().mean()))
         bound = torch.maximum(want.float().abs(), got.float().abs()) * 2.0 ** -7   # one ulp of the larger binade
