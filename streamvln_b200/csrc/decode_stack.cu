@@ -34,7 +34,7 @@
 // a barrier whose last arriver publishes a generation number to eight separate flag lines that the CTAs poll instead
 // of the arrival counter (3-6 % slower: one more L2 round trip per barrier than it saves in poll contention); dealing
 // rows round-robin (CTA c owns rows c, c + G, ...: the grid sweeps one contiguous band) instead of in contiguous
-// slices (no difference).
+// slices (no difference); 12 warps per CTA with a 16-slot ring (5 % slower: 168 registers per thread, more spills).
 // Rounding points are those of the unfused path (fused_ops.cu, kv_window.cu rope8, gemv.cu), i.e. HF's bf16
 // modules; accumulation order differs from cuBLAS, which the parity tolerance (1e-2 on logits) covers.
 #include <stdlib.h>
