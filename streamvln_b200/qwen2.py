@@ -1,11 +1,13 @@
 """Qwen2 decoder driven by libsvln kernels — the LLM arithmetic behind `generate`.
 
 Replaces HF `Qwen2ForCausalLM.forward` + `DynamicCache` + flash-attn 2 as reached from
-streamvln/model/stream_video_vln.py:340,402.  The linears (QKV, O, gate/up, down, lm_head) stay
-cuBLAS through torch ("linears stay torch/cuBLAS"); everything between them is
-hand-written sm_100a CUDA behind the C-ABI: RMSNorm(+residual), fused RoPE + KV append, tcgen05
-prefill attention, split-KV decode attention, SwiGLU, argmax.  Tokens of several streams (envs) are
-packed into one [n_tok, hidden] batch so every GEMM serves all concurrent episodes.
+streamvln/model/stream_video_vln.py:340,402.  Prefill and packed (multi-stream) forwards: the linears (QKV, O,
+gate/up, down, lm_head) are cuBLAS GEMMs through torch ("linears stay torch/cuBLAS") and
+everything between them is hand-written sm_100a CUDA behind the C-ABI: RMSNorm(+residual), fused RoPE + KV
+append, tcgen05 prefill attention, split-KV decode attention, SwiGLU, argmax.  Tokens of several streams (envs)
+are packed into one [n_tok, hidden] batch so every GEMM serves all concurrent episodes.  The single-stream decode -
+pure weight streaming - is ONE persistent kernel per generated token (`svln_decode_stack_step`, decode_stack.cu);
+2-4 streams use `svln_gemv` between the small kernels.
 """
 from __future__ import annotations
 
