@@ -164,3 +164,20 @@ def test_decode_stack_abi_argument_checks():
     assert lib.svln_pool_bilinear(None, 1, 27, 14, 3584, None, None) == -22
     assert lib.svln_pool_bilinear(None, 0, 27, 14, 3584, None, None) == 0         # nothing to do
     assert lib.svln_pool_bilinear(None, 1, 27, 14, 3583, None, None) == -22       # dim must be a multiple of 8
+
+
+def test_bench_window_alignment_and_peaks():
+    """bench.py helpers that shape the measurement: warm-up is rounded up to whole 8-turn windows (the timed region
+    starts with a window-start turn, never an all-steady-turn stretch) and the roofline denominators come from
+    MEASURED_PEAKS.json when the driver wrote it, else the documented fallback."""
+    import importlib.util
+    import sys
+
+    spec = importlib.util.spec_from_file_location("bench_mod", Path(__file__).resolve().parent.parent / "bench.py")
+    bench = importlib.util.module_from_spec(spec)
+    sys.modules["bench_mod"] = bench
+    spec.loader.exec_module(bench)
+    assert [bench.window_aligned(w) for w in (0, 1, 3, 8, 9, 16, 17)] == [8, 8, 8, 8, 16, 16, 24]
+    pk = bench.peaks()
+    assert pk["source"] in ("measured", "fallback") and pk["hbm_gbs"] > 1000 and pk["bf16_tflops"] >= pk["bf16_tflops_sustained"] > 100
+    assert bench.ENV_STEPS_PER_TURN * bench.TURNS_PER_WINDOW == 32      # num_frames
