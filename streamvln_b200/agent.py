@@ -28,6 +28,7 @@ from .model import IMAGE_TOKEN_INDEX, MEMORY_TOKEN_INDEX, StreamVLNForCausalLM
 DEFAULT_IMAGE_TOKEN = "<image>"
 DEFAULT_MEMORY_TOKEN = "<memory>"
 DEFAULT_VIDEO_TOKEN = "<video>"
+_EPISODE_NONCE = itertools.count(1)   # one per episode and process: tags the model's per-frame feature cache
 
 
 class VLNEvaluator:
@@ -75,11 +76,13 @@ class VLNEvaluator:
         self.past_key_values = None
         self.step_id = 0
         self.last_image = None
+        self.episode_id = next(_EPISODE_NONCE)
 
     def reset_memory(self):
-        """streamvln_agent.py:87-99"""
+        """streamvln_agent.py:87-99 (the reference hard-codes env 0; this resets the stream the agent last stepped)."""
         self._init_state()
-        self.model.reset_episode(0) if hasattr(self.model, "reset_episode") else self.model.reset_for_env(0)
+        env = getattr(self, "_env", 0)
+        self.model.reset_episode(env) if hasattr(self.model, "reset_episode") else self.model.reset_for_env(env)
 
     def parse_actions(self, output: str) -> List[int]:
         """streamvln_agent.py:101-107"""
@@ -122,6 +125,7 @@ class VLNEvaluator:
                 preprocessed: Optional[torch.Tensor] = None):
         """First half of `step` (streamvln_agent.py:169-240): buffer the frame, handle the window boundary, and on
         a model step build the kwargs of `model.generate`.  Returns None on a non-model step."""
+        self._env = idx
         # Step 0: observations (faked like the reference unless the caller supplies real geometry)
         camera_pose = np.eye(4) if pose is None else np.asarray(pose)
         depth = np.zeros((self.image_processor.crop_size["height"], self.image_processor.crop_size["width"]), np.float32) \
@@ -199,7 +203,7 @@ class VLNEvaluator:
             images = images.pin_memory().to(self.device, non_blocking=True)
         self.h2d_bytes = getattr(self, "h2d_bytes", 0) + input_ids.numel() * 8
         return dict(inputs=input_ids, images=images, depths=depths, poses=poses, intrinsics=intrinsics, env_id=idx,
-                    time_ids=[list(self.time_ids)], task_ids=[0], frame_ids=frame_ids, do_sample=False, num_beams=1,
+                    time_ids=[list(self.time_ids)], task_ids=[0], frame_ids=frame_ids, episode_id=self.episode_id, do_sample=False, num_beams=1,
                     max_new_tokens=self.max_new_tokens, use_cache=True, return_dict_in_generate=True,
                     past_key_values=self.past_key_values)
 

@@ -753,9 +753,12 @@ decode_stack_kernel(const __grid_constant__ StackParams p) {
             preamble_norm<NB>(p, smem, hb0, false, p.pending, p.final_norm, nullptr);
         },
         [&](int u, int n, const float (&s)[1]) {
+            // HF's lm_head is a bf16 Linear upcast with .float(): the greedy pick (and its lowest-index tie-break)
+            // is over bf16-rounded logits, as on the svln_gemv and cuBLAS paths
             const int row = v_r0 + u;
-            if (p.logits) p.logits[(int64_t)n * p.V + row] = s[0];
-            if (s[0] > best) { best = s[0]; best_i = row; }
+            const float lg = round_bf16(s[0]);
+            if (p.logits) p.logits[(int64_t)n * p.V + row] = lg;
+            if (lg > best) { best = lg; best_i = row; }
         },
         pol, p.n_layer, 0);
     {

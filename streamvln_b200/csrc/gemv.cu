@@ -81,7 +81,10 @@ gemv_kernel(const int4* __restrict__ W, const int4* __restrict__ x, const __nv_b
             for (int m = 0; m < M; ++m) {
                 // HF adds the bias inside the GEMM epilogue in fp32 and rounds once
                 const float v = acc[r][m] + b;
-                if (F32_OUT) reinterpret_cast<float*>(out)[(int64_t)m * N + n] = v;
+                // fp32 output (lm_head logits) carries bf16-ROUNDED values: HF's lm_head is a bf16 Linear whose
+                // result is upcast with .float(), so greedy argmax and its lowest-index
+                // tie-break see bf16 logits on every path (this kernel, the fused stack, cuBLAS for M > 4)
+                if (F32_OUT) reinterpret_cast<float*>(out)[(int64_t)m * N + n] = round_bf16(v);
                 else reinterpret_cast<__nv_bfloat16*>(out)[(int64_t)m * N + n] = __float2bfloat16_rn(v);
             }
         }

@@ -16,6 +16,7 @@ Two semantic modes:
 from __future__ import annotations
 
 import math
+from collections import OrderedDict
 from dataclasses import dataclass, field
 from types import SimpleNamespace
 from typing import Any, Dict, List, Optional, Sequence
@@ -47,6 +48,7 @@ class StreamVLNConfig:
     max_depth: float = 10.0
     invalid_policy: int = INVALID_KEEP
     memory_cap: int = 1568                   # max memory tokens kept (oldest dropped first)
+    feat_cache_frames: int = 160             # per-stream LRU bound of the pooled-feature cache (1.4 MB per frame at 7B)
 
     @staticmethod
     def tiny(vocab_size: int = 512, mode: str = "reference", layers: int = 2, max_pos: int = 4096) -> "StreamVLNConfig":
@@ -115,7 +117,9 @@ class StreamVLNForCausalLM:
             self.engine = Qwen2Engine(self.config.llm, self.weights, n_env=env_num, device=self.device)
         self.curr_t = [0] * env_num
         self.cache: List[Dict[str, Any]] = [dict() for _ in range(env_num)]
-        self.feat_cache: List[Dict[int, torch.Tensor]] = [dict() for _ in range(env_num)]
+        # per-frame pooled features of the CURRENT episode of each stream (an LRU; a miss only costs a re-encode)
+        self.feat_cache: List["OrderedDict[int, torch.Tensor]"] = [OrderedDict() for _ in range(env_num)]
+        self.feat_episode: List[Any] = [None] * env_num
         for e in range(env_num):
             self.engine.arena.reset_env(e)
         if self.config.mode == "slowfast":
@@ -124,30 +128,47 @@ class StreamVLNForCausalLM:
             self.sf = [SlowFastState(self, e) for e in range(env_num)]
 
     def reset_for_env(self, env_idx: int) -> None:
-        """stream_video_vln.py:477-479: forget the stream's embeds (the KV goes with `past_key_values=None`)."""
+        """stream_video_vln.py:477-479: forget the stream's embeds (the KV goes with `past_key_values=None`).
+        The reference calls this at every window boundary AND at every episode start (streamvln_eval.py:225,347), so
+        it cannot drop the per-frame feature cache (a window start re-uses its history frames); stale features
+        are excluded by the `episode_id` every request carries (see `_cache_for`)."""
         self.curr_t[env_idx] = 0
         self.cache[env_idx] = dict()
         if self.config.mode == "slowfast":
             self.sf[env_idx].reset()
             self.engine.arena.reset_env(env_idx)
-            self.feat_cache[env_idx] = dict()
 
     def reset_episode(self, env_idx: int) -> None:
         """New episode on this stream: also drop the per-frame feature cache."""
         self.reset_for_env(env_idx)
-        self.feat_cache[env_idx] = dict()
+        self.feat_cache[env_idx] = OrderedDict()
+        self.feat_episode[env_idx] = None
         self.engine.arena.reset_env(env_idx)
+
+    def _cache_for(self, env_id: int, episode_id) -> "OrderedDict[int, torch.Tensor]":
+        """Feature cache of stream env_id for the episode `episode_id` (a nonce the agent draws per episode): frame
+        ids restart at 0 with every episode, so a cache that belongs to another episode is dropped, whoever forgot
+        to call reset_episode."""
+        if self.feat_episode[env_id] != episode_id:
+            self.feat_cache[env_id] = OrderedDict()
+            self.feat_episode[env_id] = episode_id
+        return self.feat_cache[env_id]
+
+    def _cache_put(self, cache, frame_id: int, feat: torch.Tensor) -> None:
+        cache[frame_id] = feat
+        while len(cache) > self.config.feat_cache_frames:
+            cache.popitem(last=False)
 
     # ------------------------------------------------------------------ encode_rgbd
     @torch.no_grad()
     def encode_rgbd(self, images: torch.Tensor, depths, poses, intrinsics, time_ids=None, task_ids=None,
-                    env_id: int = 0, frame_ids: Optional[Sequence[int]] = None):
+                    env_id: int = 0, frame_ids: Optional[Sequence[int]] = None, episode_id=None):
         """stream_video_vln.py:102-142 for batch size 1: returns (image_features [V',196,D],
         memory_features [1, nh*196, D] or None).  `frame_ids` (optional, one global frame index per view)
         enables the per-frame pooled-feature cache."""
         assert images.shape[0] == 1, "one stream per call (the reference call sites use batch size 1)"
         V = images.shape[1]
-        feats = self._encode_views(images[0], env_id, frame_ids)
+        feats = self._encode_views(images[0], env_id, frame_ids, episode_id)
         start_idx = 0
         if time_ids is not None and time_ids[0] is not None and len(time_ids[0]):
             start_idx = time_ids[0][0]
@@ -157,27 +178,39 @@ class StreamVLNForCausalLM:
             return feats[nh:], memory
         return feats, None
 
-    def _encode_views(self, views: torch.Tensor, env_id: int, frame_ids) -> torch.Tensor:
-        if frame_ids is None:
+    def _encode_views(self, views: torch.Tensor, env_id: int, frame_ids, episode_id=None) -> torch.Tensor:
+        if frame_ids is None or self.config.mode == "slowfast":   # slowfast never looks at an old frame again
             return self.vision(views.to(self.device))
-        cache = self.feat_cache[env_id]
+        cache = self._cache_for(env_id, episode_id)
         missing = [i for i, f in enumerate(frame_ids) if f not in cache]
+        fresh = {}
         if missing:
             new = self.vision(views[missing].to(self.device))
             for j, i in enumerate(missing):
-                cache[frame_ids[i]] = new[j]
-        return torch.stack([cache[f] for f in frame_ids])
+                fresh[frame_ids[i]] = new[j]
+        out = []
+        for f in frame_ids:
+            if f in fresh:
+                out.append(fresh[f])
+            else:
+                cache.move_to_end(f)
+                out.append(cache[f])
+        for f, ft in fresh.items():
+            self._cache_put(cache, f, ft)
+        return torch.stack(out)
 
     def _prefetch_features(self, requests: Sequence[Dict[str, Any]], max_batch: int = 16) -> None:
         """Encode, in as few SigLIP batches as possible, every frame of this batch of turns that is not in the
         per-stream feature cache yet (requests that carry `frame_ids`)."""
         todo = []
+        if self.config.mode == "slowfast":
+            return
         for r in requests:
             fids, images = r.get("frame_ids"), r.get("images")
             if fids is None or images is None:
                 continue
             env = r.get("env_id", 0) or 0
-            cache = self.feat_cache[env]
+            cache = self._cache_for(env, r.get("episode_id"))
             for i, f in enumerate(fids):
                 if f not in cache and all(not (e == env and g == f) for e, g, _ in todo):
                     todo.append((env, f, images[0, i]))
@@ -187,7 +220,7 @@ class StreamVLNForCausalLM:
             part = todo[b0:b0 + max_batch]
             feats = self.vision(torch.stack([x[2].to(self.device) for x in part]))
             for (env, f, _), ft in zip(part, feats):
-                self.feat_cache[env][f] = ft
+                self._cache_put(self.feat_cache[env], f, ft)
 
     # ------------------------------------------------------------------ embed splice
     def splice(self, input_ids: Sequence[int], image_features: torch.Tensor, memory_features: Optional[torch.Tensor]) -> torch.Tensor:
@@ -262,7 +295,7 @@ class StreamVLNForCausalLM:
             else:
                 if r.get("images") is not None:
                     img_f, mem_f = self.encode_rgbd(r["images"], r.get("depths"), r.get("poses"), r.get("intrinsics"),
-                                                    time_ids, r.get("task_type"), env, r.get("frame_ids"))
+                                                    time_ids, r.get("task_type"), env, r.get("frame_ids"), r.get("episode_id"))
                     emb = self.splice(ids, img_f, mem_f)
                 else:
                     emb = self.weights.embed.index_select(0, torch.tensor(ids, dtype=torch.int64).to(self.device))

@@ -13,6 +13,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import warnings
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Sequence
 
@@ -60,9 +61,12 @@ class Qwen2Weights:
         self.layers: List[Dict[str, torch.Tensor]] = []
 
     @staticmethod
-    def random(cfg: Qwen2Config, device, seed: int = 0, std: float = 0.02, lm_head_std: Optional[float] = None) -> "Qwen2Weights":
+    def random(cfg: Qwen2Config, device, seed: int = 0, std: float = 0.02, lm_head_std: Optional[float] = None,
+               norm_std: float = 0.1) -> "Qwen2Weights":
         """Random init N(0, std) (HF initializer_range 0.02), generated on the device.  lm_head_std lets
-        tests spread the logits so that greedy argmax is not a coin flip between near-ties."""
+        tests spread the logits so that greedy argmax is not a coin flip between near-ties.  RMSNorm weights
+        are 1 + N(0, norm_std) - NOT all ones - so that a wrong norm-weight index in any kernel shows up in
+        the parity tests (trained checkpoints have far-from-unit norm weights)."""
         w = Qwen2Weights(cfg, device)
         g = torch.Generator(device=w.device).manual_seed(seed)
         D, H, KV, hd, I = cfg.hidden_size, cfg.num_attention_heads, cfg.num_key_value_heads, cfg.head_dim, cfg.intermediate_size
@@ -70,13 +74,15 @@ class Qwen2Weights:
         def rnd(*shape, s=std):
             return (torch.randn(*shape, generator=g, device=w.device, dtype=torch.float32) * s).to(torch.bfloat16)
 
+        def norm():
+            return (1.0 + torch.randn(D, generator=g, device=w.device, dtype=torch.float32) * norm_std).to(torch.bfloat16)
+
         w.embed = rnd(cfg.vocab_size, D)
         w.lm_head = rnd(cfg.vocab_size, D, s=lm_head_std or std)
-        w.final_norm = torch.ones(D, dtype=torch.bfloat16, device=w.device)
+        w.final_norm = norm()
         for _ in range(cfg.num_hidden_layers):
             w.layers.append(dict(
-                ln1=torch.ones(D, dtype=torch.bfloat16, device=w.device),
-                ln2=torch.ones(D, dtype=torch.bfloat16, device=w.device),
+                ln1=norm(), ln2=norm(),
                 wqkv=rnd((H + 2 * KV) * hd, D), bqkv=rnd((H + 2 * KV) * hd),
                 wo=rnd(D, H * hd), wgu=rnd(2 * I, D), wd=rnd(D, I)))
         return w
@@ -104,8 +110,8 @@ class Qwen2Weights:
                 wd=t(p + "mlp.down_proj.weight")))
         return w
 
-    def to_hf_state_dict(self) -> Dict[str, torch.Tensor]:
-        """Un-fuse into HF Qwen2ForCausalLM names (used by the CPU oracle to load identical weights)."""
+    def to_hf_state_dict(self, device="cpu") -> Dict[str, torch.Tensor]:
+        """Un-fuse into HF Qwen2ForCausalLM names (used by the oracle to load identical weights)."""
         cfg = self.cfg
         H, KV, hd, I = cfg.num_attention_heads, cfg.num_key_value_heads, cfg.head_dim, cfg.intermediate_size
         sd = {"model.embed_tokens.weight": self.embed, "lm_head.weight": self.lm_head, "model.norm.weight": self.final_norm}
@@ -119,7 +125,7 @@ class Qwen2Weights:
                        p + "self_attn.q_proj.bias": bq, p + "self_attn.k_proj.bias": bk, p + "self_attn.v_proj.bias": bv,
                        p + "self_attn.o_proj.weight": L["wo"], p + "mlp.gate_proj.weight": gate,
                        p + "mlp.up_proj.weight": up, p + "mlp.down_proj.weight": L["wd"]})
-        return {k: v.detach().cpu() for k, v in sd.items()}
+        return {k: v.detach().to(device) for k, v in sd.items()}
 
 
 @dataclass
@@ -157,6 +163,8 @@ class Qwen2Engine:
         self._pgraphs: Dict[tuple, "_PrefillGraph"] = {}
         self._pseen: Dict[tuple, int] = {}
         self._prof_flops = 0.0
+        self._warned_clamp = False
+        self._eos_pin: Optional[torch.Tensor] = None
 
     # ------------------------------------------------------------------ small kernels
     def _rmsnorm(self, x: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
@@ -233,6 +241,11 @@ class Qwen2Engine:
         for c in chunks:
             envs += [c.env] * c.n_q
             poss += list(range(c.kv_len - c.n_q, c.kv_len))
+            # the kernels drop an append whose stream / row is out of range (kv_window.cu), so the host refuses it here
+            if not 0 <= c.env < self.arena.n_env:
+                raise ValueError(f"stream {c.env} outside the arena (n_env = {self.arena.n_env})")
+            if c.n_q < 1 or c.kv_len < c.n_q:
+                raise ValueError(f"stream {c.env}: bad chunk (n_q = {c.n_q}, kv_len = {c.kv_len})")
             if c.kv_len > self.arena.max_len - 1:  # the last row is the CUDA-graph capture scratch row
                 raise ValueError(f"stream {c.env}: {c.kv_len} tokens exceed the arena ({self.arena.max_len - 1} usable rows)")
         assert len(envs) == n_tok
@@ -306,6 +319,15 @@ class Qwen2Engine:
         for e, env in zip(embeds, envs):
             chunks.append(Chunk(env, q0, e.shape[0], self.arena.lens[env] + e.shape[0]))
             q0 += e.shape[0]
+        # HF would run to max_new_tokens (the agent passes 10000, streamvln_agent.py:244) and rely on EOS; the arena
+        # is finite, so the budget is clamped to the rows left (the last generated token is never fed back)
+        headroom = min(self.arena.max_len - 1 - c.kv_len for c in chunks) + 1
+        if max_new_tokens > headroom:
+            if eos_token_id is None and not self._warned_clamp:
+                warnings.warn(f"max_new_tokens={max_new_tokens} exceeds the KV arena headroom ({headroom}) and no eos_token_id "
+                              "is set: generation is clamped to the arena", stacklevel=2)
+                self._warned_clamp = True
+            max_new_tokens = max(headroom, 1)
         h = torch.cat(list(embeds), dim=0) if B > 1 else embeds[0].clone()
         logits = self.forward(h, chunks)
         tok = self.argmax(logits)
@@ -313,28 +335,35 @@ class Qwen2Engine:
         if max_new_tokens > 1:
             # bench.py's profiling pass times the launches with CUDA events, which cannot sit inside a replayed graph
             runner = self._decode_runner(envs, use_graph and self.use_graphs and self.prof is None)
-            alive = None
-            for _ in range(max_new_tokens - 1):
-                if eos_token_id is not None:
-                    done = tok == eos_token_id
-                    alive = ~done if alive is None else alive & ~done
-                    if not bool(alive.any()):
+            if eos_token_id is None:
+                for _ in range(max_new_tokens - 1):
+                    tok = runner.step(tok)
+                    out.append(tok)
+            else:
+                # EOS is checked with a lag of one step: token i travels to pinned host memory asynchronously and is
+                # looked at only after step i+1 has been queued, so the device never waits for the host.  The price
+                # is at most one surplus step per turn, un-fed by the length roll-back below.
+                watch = _EosWatch(self, B, eos_token_id)
+                watch.post(tok)
+                for _ in range(max_new_tokens - 1):
+                    if watch.all_done(lag=1):
                         break
-                tok = runner.step(tok)
-                out.append(tok)
+                    tok = runner.step(tok)
+                    out.append(tok)
+                    watch.post(tok)
             runner.finish()
         seqs = torch.stack(out, dim=1)  # [B, n_steps]
+        if eos_token_id is None:
+            return [seqs[b] for b in range(B)]
+        seqs_h = seqs.cpu()              # the turn's D2H read (the agent needs the ids on the host anyway)
         res = []
         for b in range(B):
-            s = seqs[b]
-            if eos_token_id is not None:
-                hit = (s == eos_token_id).nonzero()
-                if hit.numel():
-                    n = int(hit[0]) + 1
-                    s = s[:n]
-                    # tokens fed after this stream's EOS were appended to its cache: roll the length back
-                    self.arena.lens[envs[b]] -= (seqs.shape[1] - n)
-            res.append(s)
+            hit = (seqs_h[b] == eos_token_id).nonzero()
+            n = int(hit[0]) + 1 if hit.numel() else seqs.shape[1]
+            # tokens fed after this stream's EOS were appended to its cache: roll the length back, so the cache holds
+            # L_embeds + n_gen - 1 rows exactly as HF's does
+            self.arena.lens[envs[b]] -= (seqs.shape[1] - n)
+            res.append(seqs[b, :n])
         return res
 
     def _decode_runner(self, envs: Sequence[int], use_graph: bool) -> "_DecodeRunner":
@@ -420,6 +449,36 @@ class Qwen2Engine:
         h, pending = self._layers(h, state.seq_env, state.tok_pos, attn)
         x = self._add_rmsnorm(h, pending, self.w.final_norm)
         return self.argmax(self._linear(x, self.w.lm_head, None, f32_out=True))
+
+
+class _EosWatch:
+    """Host-side view of which streams have emitted EOS, fed by asynchronous D2H copies of each step's tokens."""
+
+    SLOTS = 4
+
+    def __init__(self, eng: "Qwen2Engine", B: int, eos: int):
+        self.eos = eos
+        if eng._eos_pin is None or eng._eos_pin.shape[1] < B:
+            eng._eos_pin = torch.empty(self.SLOTS, max(B, 8), dtype=torch.int64).pin_memory()
+        self.pin, self.B = eng._eos_pin, B
+        self.done = torch.zeros(B, dtype=torch.bool)
+        self.pending = []   # [(event, slot)] oldest first
+        self.n_posted = 0
+
+    def post(self, tok: torch.Tensor) -> None:
+        slot = self.n_posted % self.SLOTS
+        self.n_posted += 1
+        self.pin[slot, :self.B].copy_(tok, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self.pending.append((ev, slot))
+
+    def all_done(self, lag: int) -> bool:
+        while len(self.pending) > lag:
+            ev, slot = self.pending.pop(0)
+            ev.synchronize()
+            self.done |= self.pin[slot, :self.B] == self.eos
+        return bool(self.done.all())
 
 
 class _DecodeState:
