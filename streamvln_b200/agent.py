@@ -200,7 +200,8 @@ class VLNEvaluator:
         # Step 4: generate (:242-246).  One pinned-memory H2D per turn for the frames.
         if not images.is_cuda:
             self.h2d_bytes = images.numel() * images.element_size()
-            images = images.pin_memory().to(self.device, non_blocking=True)
+            if self.device.type == "cuda":   # (a CPU `device` only occurs in the host-logic tests, with a recording model)
+                images = images.pin_memory().to(self.device, non_blocking=True)
         self.h2d_bytes = getattr(self, "h2d_bytes", 0) + input_ids.numel() * 8
         return dict(inputs=input_ids, images=images, depths=depths, poses=poses, intrinsics=intrinsics, env_id=idx,
                     time_ids=[list(self.time_ids)], task_ids=[0], frame_ids=frame_ids, episode_id=self.episode_id, do_sample=False, num_beams=1,

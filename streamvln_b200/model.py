@@ -56,6 +56,18 @@ class StreamVLNConfig:
         return StreamVLNConfig(llm=llm, vision=VisionConfig.tiny(llm.hidden_size), mode=mode)
 
 
+def uncached_tail(total_len: int, past_len: int):
+    """Rows of the stream's embed cache that one `generate` call runs through the LLM: (first_row, n_rows).
+    The reference passes the FULL embed cache to HF generate together with the carried KV cache; HF 4.45.1 sets
+    cache_position = arange(total_len)[past_len:] and the reference's prepare_inputs_for_generation override keeps
+    `inputs_embeds[:, -len(cache_position):]` (all of them when cache_position[0] == 0)
+    (streamvln/model/stream_video_vln.py:449-453; pinned by tests/golden/ref_tail_rule.npz)."""
+    n = total_len - past_len
+    if n <= 0:
+        raise ValueError("nothing to run: the KV cache already covers every embedded token")
+    return past_len, n
+
+
 class KvHandle:
     """Opaque `past_key_values`: the arena owns the data; the handle only names the stream."""
 
@@ -311,11 +323,8 @@ class StreamVLNForCausalLM:
                 past_len = self.engine.arena.lens[env] if past is not None else 0
                 if past is None:
                     self.engine.arena.reset_env(env)
-                # HF: cache_position = arange(L_full)[past_len:] -> only the un-cached tail is run
-                n_tail = c["len"] - past_len
-                if n_tail <= 0:
-                    raise ValueError("nothing to run: the KV cache already covers every embedded token")
-                tail = emb[emb.shape[0] - n_tail:] if n_tail <= emb.shape[0] else torch.cat(c["chunks"])[past_len:]
+                first, n_tail = uncached_tail(c["len"], past_len)
+                tail = emb[emb.shape[0] - n_tail:] if n_tail <= emb.shape[0] else torch.cat(c["chunks"])[first:]
             tails.append(tail)
             envs.append(env)
             max_new.append(int(r.get("max_new_tokens", 20)))

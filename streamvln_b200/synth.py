@@ -37,6 +37,20 @@ def pose_matrix(x: float, y: float, yaw: float, cam_h: float = CAM_HEIGHT) -> np
     return (tf @ AXIS_ALIGN).astype(np.float32)
 
 
+def preprocess_depth(depth01: np.ndarray, min_depth: float = 0.0, max_depth: float = 10.0, size: int = GRID) -> np.ndarray:
+    """Habitat depth in [0,1] -> metres on the size x size processor grid, as the reference's eval loop does it
+    (streamvln_eval.py:254-256 scale to metres then millimetres, :276 uint16 truncation, :126-135 PIL NEAREST squash to
+    384x384 and / 1000; `filter_depth(blur_type=None)` of depth-camera-filtering is not reproduced).  Host reference of
+    `svln_preprocess_depth`; pinned by tests/golden/ref_geometry.npz."""
+    d = np.asarray(depth01, np.float32)
+    d = d.reshape(d.shape[:2])
+    mm = ((d * np.float32(max_depth - min_depth) + np.float32(min_depth)) * np.float32(1000)).astype(np.uint16)
+    h, w = mm.shape
+    iy = ((np.arange(size) + 0.5) * (h / size)).astype(np.int64)     # Pillow NEAREST: (int)((i + 0.5) * scale)
+    ix = ((np.arange(size) + 0.5) * (w / size)).astype(np.int64)
+    return (mm[iy][:, ix] / 1000).astype(np.float32)
+
+
 def action_walk(n_steps: int, rng: np.random.Generator):
     """Seeded R2R-style walk: p(forward)=.6, p(left)=p(right)=.2.  Returns actions and poses."""
     acts = rng.choice(np.array([1, 2, 3]), size=n_steps, p=[0.6, 0.2, 0.2])
