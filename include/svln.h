@@ -188,6 +188,33 @@ int svln_kv_rerotate(const svln_kv_arena* arena, int env, int row0, int n_rows,
                      const int32_t* delta_pos, const float* cos_delta, const float* sin_delta,
                      int n_delta, svln_stream_t stream);
 
+/* Batched, device-side planning of the slow-memory eviction: every stream that slides its window this turn is one
+ * job; nothing visits the host between the dedup and the compaction.  No reference counterpart (the released code
+ * drops the whole cache per window, stream_video_vln.py:473-479): this is the glue between (1) and (2), to the spec in
+ * DESIGN.md section 4 (oracle/slowfast.py::_evict).  Per job j, jobs[j*SVLN_SF_JOB_WORDS + w] (device i32) holds
+ *   w=0 stream (arena env)      w=1 prefix rows P           w=2 memory tokens M (before)
+ *   w=3 first row of the evicted turn (== P + M)            w=4 offset of its image rows inside the turn
+ *   w=5 rows of the evicted turn w=6 cache length L          w=7 frame time of the evicted turn
+ *   w=8 ring slot of the turn's voxel keys                   w=9 offset of the job's segment in cand_key / cand_t
+ * State: mem_key [n_env, mem_cap] i64, mem_t [n_env, mem_cap] i32 (slow-memory voxel keys / frame times, oldest
+ * first), turn_key [n_env, n_slots, tokens_per_frame] i64 (keys of the live turns' image tokens).
+ *   svln_sf_gather_candidates: cand[off .. off+M+tpf) = [memory | evicted turn] of every job (the dedup segments that
+ *     svln_keep_latest takes);
+ *   svln_sf_evict_plan (after svln_keep_latest -> mask): survivors in stable order, at most mem_cap (oldest dropped),
+ *     become the new memory; src_row [n_jobs, max_len] = the source map of svln_kv_compact
+ *     ([0,P) identity | survivors | every row behind the evicted turn); plan_out [4, n_jobs] i32 = first moved row,
+ *     new cache length, new memory size, survivors before the cap - rows 0 and 1 are svln_kv_compact's
+ *     first_row / new_len arguments as they stand. */
+#define SVLN_SF_JOB_WORDS 10
+int svln_sf_gather_candidates(const int32_t* jobs, int n_jobs, const int64_t* mem_key,
+                              const int32_t* mem_t, int mem_cap, const int64_t* turn_key, int n_slots,
+                              int tokens_per_frame, int64_t* cand_key, int32_t* cand_t,
+                              svln_stream_t stream);
+int svln_sf_evict_plan(const int32_t* jobs, int n_jobs, const uint8_t* mask, const int64_t* cand_key,
+                       const int32_t* cand_t, int mem_cap, int tokens_per_frame, int max_len,
+                       int64_t* mem_key, int32_t* mem_t, int32_t* src_row, int32_t* plan_out,
+                       svln_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * (3) Per-step attention over [pruned memory | window KV | new tokens]; replaces flash-attn 2
  * (selected at streamvln_eval.py:526) for HF Qwen2 attention (reached via

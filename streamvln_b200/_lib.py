@@ -15,6 +15,7 @@ SVLN_OK = 0
 INVALID_KEEP = 0
 INVALID_DROP = 1
 KEY_INVALID = -1
+SF_JOB_WORDS = 10   # SVLN_SF_JOB_WORDS
 
 _ERRNAMES = {-22: "EINVAL", -12: "ENOMEM", -34: "ERANGE", -5: "EIO(CUDA)"}
 
@@ -80,6 +81,8 @@ PROTOTYPES = {
     "svln_kv_append_rope": (_i, [_arena_p, _i, _vp, _i, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp]),
     "svln_kv_compact": (_i, [_arena_p, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _i, _vp]),
     "svln_kv_rerotate": (_i, [_arena_p, _i, _i, _i, _vp, _vp, _vp, _i, _vp]),
+    "svln_sf_gather_candidates": (_i, [_vp, _i, _vp, _vp, _i, _vp, _i, _i, _vp, _vp, _vp]),
+    "svln_sf_evict_plan": (_i, [_vp, _i, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "svln_attn_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "svln_attn_decode": (_i, [_arena_p, _i, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp, _sz,
                               _vp, _vp]),

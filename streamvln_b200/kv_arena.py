@@ -34,6 +34,30 @@ def delta_rope_tables(n_delta: int, head_dim: int, theta: float):
     return ang.cos().float(), ang.sin().float()
 
 
+class _Lens(list):
+    """Host-side cache lengths.  A device-side eviction (slowfast.py) owes the host its data-dependent new lengths
+    until the turn's D2H read has happened; `pending` (a callable) settles that debt on the first access."""
+
+    pending = None
+
+    def _settle(self):
+        fn, self.pending = self.pending, None
+        if fn is not None:
+            fn()
+
+    def __getitem__(self, i):
+        self._settle()
+        return list.__getitem__(self, i)
+
+    def __setitem__(self, i, v):
+        self._settle()
+        list.__setitem__(self, i, v)
+
+    def __iter__(self):
+        self._settle()
+        return list.__iter__(self)
+
+
 class KvArena:
     def __init__(self, n_env: int, n_layer: int, n_kv_head: int, head_dim: int, max_len: int,
                  rope_theta: float = 1e6, device="cuda"):
@@ -53,7 +77,7 @@ class KvArena:
         self.cos, self.sin = cos.to(self.device).contiguous(), sin.to(self.device).contiguous()
         cd, sd = delta_rope_tables(max_len, head_dim, rope_theta)
         self.cos_delta, self.sin_delta = cd.to(self.device).contiguous(), sd.to(self.device).contiguous()
-        self.lens = [0] * n_env  # host-side cache lengths (rows in use per stream)
+        self.lens = _Lens([0] * n_env)  # host-side cache lengths (rows in use per stream)
         # attention scratch (split-KV partials), allocated ONCE: captured CUDA graphs hold its address
         self._attn_ws_rows = max(256, 4 * n_env)
         self._attn_ws = torch.empty(self.lib.svln_attn_workspace_bytes(self._attn_ws_rows, 32, head_dim, max_len),

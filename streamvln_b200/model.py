@@ -69,16 +69,23 @@ def uncached_tail(total_len: int, past_len: int):
 
 
 class KvHandle:
-    """Opaque `past_key_values`: the arena owns the data; the handle only names the stream."""
+    """Opaque `past_key_values`: the arena owns the data; the handle only names the stream.  The length is read
+    from the arena on demand (in slowfast mode a device-side eviction may still owe it to the host)."""
 
-    def __init__(self, env: int, length: int):
-        self.env, self.length = env, length
+    def __init__(self, env: int, arena):
+        self.env, self._arena, self._length = env, arena, None
+
+    @property
+    def length(self) -> int:
+        if self._length is None:
+            self._length = self._arena.lens[self.env]
+        return self._length
 
     def get_seq_length(self) -> int:
         return self.length
 
     def __repr__(self):
-        return f"KvHandle(env={self.env}, length={self.length})"
+        return f"KvHandle(env={self.env})"
 
 
 class GenerateOutput(SimpleNamespace):
@@ -135,9 +142,10 @@ class StreamVLNForCausalLM:
         for e in range(env_num):
             self.engine.arena.reset_env(e)
         if self.config.mode == "slowfast":
-            from .slowfast import SlowFastState
+            from .slowfast import SlowFastBatch
 
-            self.sf = [SlowFastState(self, e) for e in range(env_num)]
+            self.sfb = SlowFastBatch(self, max(env_num, self.engine.arena.n_env))
+            self.sf = self.sfb.states
 
     def reset_for_env(self, env_idx: int) -> None:
         """stream_video_vln.py:477-479: forget the stream's embeds (the KV goes with `past_key_values=None`).
@@ -291,20 +299,25 @@ class StreamVLNForCausalLM:
         """Several streams' turns in one packed forward (one request per env_id; same kwargs as `generate`).
         This is what lets 64 concurrent episodes share every GEMM."""
         tails, envs, max_new = [], [], []
-        self._prefetch_features(requests)
+        slowfast = self.config.mode == "slowfast"
+        ids_list = []
         for r in requests:
-            r = dict(r)
             if "inputs_embeds" in r:
                 raise NotImplementedError("`inputs_embeds` is not supported")  # stream_video_vln.py:369-370
             if r.get("do_sample", False) or r.get("num_beams", 1) != 1:
                 raise NotImplementedError("only greedy decoding (do_sample=False, num_beams=1) is supported")
-            env = r.get("env_id", 0) or 0
             ids = r["inputs"]
-            ids = ids.reshape(-1).tolist() if torch.is_tensor(ids) else list(ids)
-            time_ids = r.get("time_ids")
-            if self.config.mode == "slowfast":
-                tail = self.sf[env].prepare_turn(ids, r)
-            else:
+            ids_list.append(ids.reshape(-1).tolist() if torch.is_tensor(ids) else list(ids))
+            envs.append(r.get("env_id", 0) or 0)
+            max_new.append(int(r.get("max_new_tokens", 20)))
+        if len(set(envs)) != len(envs):
+            raise ValueError("one request per env_id in a batch")
+        if slowfast:
+            tails = self.sfb.prepare_turns(requests, ids_list)
+        else:
+            self._prefetch_features(requests)
+            for r, ids, env in zip(requests, ids_list, envs):
+                time_ids = r.get("time_ids")
                 if r.get("images") is not None:
                     img_f, mem_f = self.encode_rgbd(r["images"], r.get("depths"), r.get("poses"), r.get("intrinsics"),
                                                     time_ids, r.get("task_type"), env, r.get("frame_ids"), r.get("episode_id"))
@@ -324,21 +337,17 @@ class StreamVLNForCausalLM:
                 if past is None:
                     self.engine.arena.reset_env(env)
                 first, n_tail = uncached_tail(c["len"], past_len)
-                tail = emb[emb.shape[0] - n_tail:] if n_tail <= emb.shape[0] else torch.cat(c["chunks"])[first:]
-            tails.append(tail)
-            envs.append(env)
-            max_new.append(int(r.get("max_new_tokens", 20)))
-        if len(set(envs)) != len(envs):
-            raise ValueError("one request per env_id in a batch")
+                tails.append(emb[emb.shape[0] - n_tail:] if n_tail <= emb.shape[0] else torch.cat(c["chunks"])[first:])
         n_new = max(max_new)
         seqs = self.engine.generate(tails, envs, n_new, self.config.eos_token_id)
-        outs = []
+        outs, evict = [], []
         for r, env, s, mn in zip(requests, envs, seqs, max_new):
             if s.shape[0] > mn:  # a shorter budget than the batch maximum: un-feed the surplus tokens
                 self.engine.arena.lens[env] -= s.shape[0] - mn
                 s = s[:mn]
-            if self.config.mode == "slowfast":
-                self.sf[env].finish_turn(int(s.shape[0]))
-            outs.append(GenerateOutput(sequences=s.unsqueeze(0),
-                                       past_key_values=KvHandle(env, self.engine.arena.lens[env])))
+            if slowfast and self.sf[env].finish_turn(int(s.shape[0])):
+                evict.append(env)
+            outs.append(GenerateOutput(sequences=s.unsqueeze(0), past_key_values=KvHandle(env, self.engine.arena)))
+        if evict:
+            self.sfb.evict(evict)   # all streams that slide this turn: one batched, device-side pass
         return outs
