@@ -164,6 +164,7 @@ class Qwen2Engine:
         self._pseen: Dict[tuple, int] = {}
         self._prof_flops = 0.0
         self._warned_clamp = False
+        self.logits_log: List[torch.Tensor] = []
         self._eos_pin: Optional[torch.Tensor] = None
 
     # ------------------------------------------------------------------ small kernels
@@ -332,6 +333,9 @@ class Qwen2Engine:
         logits = self.forward(h, chunks)
         tok = self.argmax(logits)
         out = [tok]
+        keep = self.keep_decode_logits
+        if keep:
+            self.logits_log = [logits.clone()]   # per generated token: fp32 logits [B, vocab] (tests and debugging)
         if max_new_tokens > 1:
             # bench.py's profiling pass times the launches with CUDA events, which cannot sit inside a replayed graph
             runner = self._decode_runner(envs, use_graph and self.use_graphs and self.prof is None)
@@ -339,6 +343,8 @@ class Qwen2Engine:
                 for _ in range(max_new_tokens - 1):
                     tok = runner.step(tok)
                     out.append(tok)
+                    if keep:
+                        self.logits_log.append(runner.last_logits())
             else:
                 # EOS is checked with a lag of one step: token i travels to pinned host memory asynchronously and is
                 # looked at only after step i+1 has been queued, so the device never waits for the host.  The price
@@ -351,6 +357,8 @@ class Qwen2Engine:
                     tok = runner.step(tok)
                     out.append(tok)
                     watch.post(tok)
+                    if keep:
+                        self.logits_log.append(runner.last_logits())
             runner.finish()
         seqs = torch.stack(out, dim=1)  # [B, n_steps]
         if eos_token_id is None:
@@ -448,7 +456,10 @@ class Qwen2Engine:
             self.launches += 2
         h, pending = self._layers(h, state.seq_env, state.tok_pos, attn)
         x = self._add_rmsnorm(h, pending, self.w.final_norm)
-        return self.argmax(self._linear(x, self.w.lm_head, None, f32_out=True))
+        lg = self._linear(x, self.w.lm_head, None, f32_out=True)
+        if self.keep_decode_logits:
+            state.last_logits = lg
+        return self.argmax(lg)
 
 
 class _EosWatch:
@@ -492,6 +503,7 @@ class _DecodeState:
         self.tok_pos = torch.empty(B, dtype=torch.int32, device=dev)
         self.max_kv = eng.arena.max_len
         self.stack = None  # svln_decode_stack descriptor + its buffers (built on first use)
+        self.last_logits = None  # launch-per-op path with keep_decode_logits: fp32 logits of the last step
         self.host_len = max([eng.arena.lens[e] for e in envs] + [0]) + 1   # host mirror of kv_len (profiling only)
 
 
@@ -525,6 +537,12 @@ class _DecodeRunner:
     def finish(self) -> None:
         for e in self.envs:
             self.eng.arena.lens[e] += self.steps
+
+    def last_logits(self) -> Optional[torch.Tensor]:
+        """fp32 logits [B, vocab] of the last step (only with eng.keep_decode_logits; tests and debugging)."""
+        st = self.graph.state if self.graph is not None else self.state
+        lg = st.stack_logits if st.stack is not None else st.last_logits
+        return None if lg is None else lg.clone()
 
 
 class _DecodeGraph:
