@@ -1,5 +1,5 @@
 """Per-kernel roofline measurements at the batched shapes of BASELINE.json configs[2]/[4] (64 concurrent
-episodes), CUDA events on the launching stream, inputs larger than the 126 MB L2.  Used by bench.py
+episodes), CUDA events on the launching stream, L2 flushed before every timed call.  Used by bench.py
 (`kernels` key) and scripts; algorithmic bytes / FLOPs per unit are SURVEY.md §8d's figures.
 """
 from __future__ import annotations
@@ -12,22 +12,32 @@ import torch
 KV_BYTES_PER_TOKEN = 2 * 28 * 4 * 128 * 2  # 57 344 B: K+V, 28 layers, 4 kv heads, 128 dims, bf16
 
 
+_FLUSH = None
+
+
 def _time(fn: Callable[[], None], iters: int = 10, warmup: int = 3) -> float:
-    """average milliseconds per call (CUDA events on the current stream)"""
+    """average milliseconds per call: one CUDA-event pair per call on the current stream, with the 126 MB L2 flushed
+    (a 256 MB buffer rewritten) before every timed call, so no call finds its inputs cached by the previous one"""
     import os
 
+    global _FLUSH
     if os.environ.get("SVLN_MICRO_ITERS"):  # profiling runs: launch each kernel only a couple of times
         iters, warmup = int(os.environ["SVLN_MICRO_ITERS"]), 1
+    if _FLUSH is None:
+        _FLUSH = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     for _ in range(warmup):
         fn()
     torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
+    pairs = []
     for _ in range(iters):
+        _FLUSH.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
         fn()
-    e1.record()
+        e1.record()
+        pairs.append((e0, e1))
     torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / iters
+    return sum(a.elapsed_time(b) for a, b in pairs) / iters
 
 
 def _row(name, bound, work, ms, peak, unit, note=""):

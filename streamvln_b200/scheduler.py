@@ -121,9 +121,13 @@ class BatchedEvaluator:
 
 
 def run_episodes(ev: BatchedEvaluator, episodes: Sequence[dict], frame_source: Callable[[int, int], np.ndarray],
-                 num_future_steps: int = 4) -> List[EpisodeResult]:
+                 num_future_steps: int = 4, resident_source: Optional[Callable[[int, int], torch.Tensor]] = None,
+                 geom_source: Optional[Callable[[int, int], dict]] = None) -> List[EpisodeResult]:
     """Stream `episodes` (dicts with id, length, instruction) through the E slots of `ev`, refilling a slot as soon
-    as its episode ends.  frame_source(episode_id, step) -> uint8 HxWx3 frame."""
+    as its episode ends (the reference runs them one after another per rank, streamvln_eval.py:218-350).
+    frame_source(episode_id, step) -> uint8 HxWx3 host frame; resident_source(episode_id, step) -> preprocessed
+    [3,384,384] device tensor (frames already in HBM; frame_source is then unused); geom_source(episode_id, step) ->
+    dict(depth, pose, intrinsic) for the slowfast mode."""
     queue = list(episodes)
     slots: Dict[int, dict] = {}
     done: List[EpisodeResult] = []
@@ -140,8 +144,13 @@ def run_episodes(ev: BatchedEvaluator, episodes: Sequence[dict], frame_source: C
             live = by_phase[run_model]
             if not live:
                 continue
-            frames = {i: frame_source(slots[i]["ep"]["id"], slots[i]["step"]) for i in live}
-            acts = ev.step_all(live, frames, {i: slots[i]["ep"]["instruction"] for i in live}, run_model)
+            geom = None if geom_source is None else {i: geom_source(slots[i]["ep"]["id"], slots[i]["step"]) for i in live}
+            if resident_source is not None:
+                pre = {i: resident_source(slots[i]["ep"]["id"], slots[i]["step"]) for i in live} if run_model else None
+                acts = ev.step_all(live, None, {i: slots[i]["ep"]["instruction"] for i in live}, run_model, geom, pre)
+            else:
+                frames = {i: frame_source(slots[i]["ep"]["id"], slots[i]["step"]) for i in live}
+                acts = ev.step_all(live, frames, {i: slots[i]["ep"]["instruction"] for i in live}, run_model, geom)
             for i in live:
                 s = slots[i]
                 if i in acts:

@@ -167,9 +167,9 @@ def test_decode_stack_abi_argument_checks():
 
 
 def test_bench_window_alignment_and_peaks():
-    """bench.py helpers that shape the measurement: warm-up is rounded up to whole 8-turn windows (the timed region
-    starts with a window-start turn, never an all-steady-turn stretch) and the roofline denominators come from
-    MEASURED_PEAKS.json when the driver wrote it, else the documented fallback."""
+    """bench.py helpers that shape the measurement: one bench step is a whole 32-frame window (8 turns, one of them the
+    window-start re-prefill), the CPU arm prices a window from the turn it sampled, and the roofline denominators come
+    from MEASURED_PEAKS.json when the driver wrote it, else the documented fallback."""
     import importlib.util
     import sys
 
@@ -178,6 +178,12 @@ def test_bench_window_alignment_and_peaks():
     sys.modules["bench_mod"] = bench
     spec.loader.exec_module(bench)
     assert [bench.window_aligned(w) for w in (0, 1, 3, 8, 9, 16, 17)] == [8, 8, 8, 8, 16, 16, 24]
+    assert bench.ENV_STEPS_PER_STEP == 32 and "window" in bench.STEP_DEF
+    last = {"steady": 1.0, "window_start": 9.0}
+    assert bench._window_seconds({"kind": "steady", "seconds": 2.0}, last) == 7 * 2.0 + 9.0
+    assert bench._window_seconds({"kind": "window_start", "seconds": 5.0}, last) == 7 * 1.0 + 5.0
+    t, src = bench.stack_traffic()
+    assert t is None or (t > 1e9 and src)
     pk = bench.peaks()
     assert pk["source"] in ("measured", "fallback") and pk["hbm_gbs"] > 1000 and pk["bf16_tflops"] >= pk["bf16_tflops_sustained"] > 100
     assert bench.ENV_STEPS_PER_TURN * bench.TURNS_PER_WINDOW == 32      # num_frames
