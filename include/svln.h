@@ -134,6 +134,13 @@ int svln_preprocess_rgb(const uint8_t* rgb, int n, int H, int W, int out_h, int 
                         const int32_t* ycnt, const int32_t* ykk, int yksize, void* workspace,
                         size_t workspace_bytes, float* out, svln_stream_t stream);
 
+/* Depth frame preprocessing, replacing the host path of the Habitat evaluator (streamvln_eval.py:254-256 depth in [0,1]
+ * -> metres -> millimetres, :276 uint16 truncation, :126-135 Pillow NEAREST squash to the processor grid and / 1000;
+ * depth-camera-filtering's filter_depth(blur_type=None) is not reproduced).  depth01 [n,H,W] f32 -> out [n,out_h,out_w]
+ * f32 metres, bit-exact with that host arithmetic (tests/golden/ref_geometry.npz). */
+int svln_preprocess_depth(const float* depth01, int n, int H, int W, int out_h, int out_w, float min_depth,
+                          float max_depth, float* out, svln_stream_t stream);
+
 /* Device-side embed splice, replacing the Python loop of torch.where/.tolist()/torch.cat in
  * prepare_inputs_labels_for_multimodal (stream_video_vln.py:182-238).  row_src[r] >= 0 selects
  * row row_src[r] of `embed_table` (token embedding); row_src[r] < 0 selects row (-row_src[r]-1)

@@ -76,6 +76,7 @@ PROTOTYPES = {
                                    _vp, _sz, _vp, _vp, _vp, _vp, _vp, _vp]),
     "svln_preprocess_workspace_bytes": (_sz, [_i, _i, _i]),
     "svln_preprocess_rgb": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _vp, _sz, _vp, _vp]),
+    "svln_preprocess_depth": (_i, [_vp, _i, _i, _i, _i, _i, _f, _f, _vp, _vp]),
     "svln_splice_rows": (_i, [_vp, _vp, _vp, _i64, _i64, _vp, _vp]),
     "svln_kv_arena_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "svln_kv_append_rope": (_i, [_arena_p, _i, _vp, _i, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp]),

@@ -23,6 +23,14 @@ int check_launch(const char* what) {
     return SVLN_OK;
 }
 
+bool first_use_on_device(unsigned long long* mask) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+    if ((*mask >> dev) & 1ull) return false;
+    *mask |= 1ull << dev;
+    return true;
+}
+
 int sm_count() {
     static int cached[64] = {0};
     int dev = 0;

@@ -124,10 +124,9 @@ int svln_attn_decode(const svln_kv_arena* arena, int layer, const void* q, int n
     p.part_m = p.part_o + slots * DROWS * HD;
     p.part_l = p.part_m + slots * DROWS;
     p.out = (__nv_bfloat16*)out;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static unsigned long long attr_set = 0;
+    if (first_use_on_device(&attr_set)) {
         SVLN_CUDA(cudaFuncSetAttribute(attn_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DEC_SMEM));
-        attr_set = true;
     }
     dim3 grid(p.n_splits, arena->n_kv_head, (unsigned)groups);
     attn_decode_kernel<<<grid, DWARPS * 32, DEC_SMEM, (cudaStream_t)stream>>>(p);

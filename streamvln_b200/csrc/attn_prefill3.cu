@@ -1,6 +1,6 @@
 // Dense prefill attention, operands A in tensor memory (tcgen05.mma "TS" form): Q and P never touch smem.
 //
-// Why: the SS kernels (attn_prefill.cu, attn_prefill2.cu) are bound by SHARED-MEMORY bandwidth, not by the
+// Why: the SS-form kernels of round 1 (both operands from shared memory; removed) were bound by SHARED-MEMORY bandwidth, not by the
 // tensor pipe, MUFU or L2 (profiles/README.md): per 128-key tile the tensor core re-reads Q (32 KB) and P
 // (32 KB) from smem besides K and V, the softmax writes P (32 KB) and TMA writes K/V (64 KB) - 224 KB per
 // 1024 MMA cycles against ~128 B/clk.  Here Q is stored to TMEM once (tcgen05.st) and P overwrites the
@@ -839,12 +839,11 @@ int prefill3_launch(const svln_kv_arena* arena, int layer, const void* q, int n_
     CUtensorMap map;
     int rc = get_kv_map(arena, P3_BN, &map);
     if (rc) return rc;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static unsigned long long attr_set = 0;
+    if (first_use_on_device(&attr_set)) {
         SVLN_CUDA(cudaFuncSetAttribute(attn_prefill3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, P3_SMEM));
         SVLN_CUDA(cudaFuncSetAttribute(attn_prefill3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, P3_SMEM));
         SVLN_CUDA(cudaFuncSetAttribute(attn_prefill3p_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P3P_SMEM));
-        attr_set = true;
     }
     // measured on B200: the multicast pair is ~5 % SLOWER than the plain kernel at the 64-stream shapes (L2 already
     // serves the repeated K/V tiles; the pair adds cluster barriers and lock-step) - opt-in via SVLN_PF_CLUSTER=1
@@ -857,8 +856,15 @@ int prefill3_launch(const svln_kv_arena* arena, int layer, const void* q, int n_
         p.n_q_head = n_q_head; p.n_kv_head = arena->n_kv_head; p.n_layer = arena->n_layer; p.layer = layer;
         p.max_len = arena->max_len;
         p.scale_log2 = scale * 1.4426950408889634f;
-        p.debug = getenv("SVLN_PF_DEBUG") ? atoi(getenv("SVLN_PF_DEBUG")) : 0;
-        p.trace = getenv("SVLN_PF_TRACE") ? (long long*)strtoull(getenv("SVLN_PF_TRACE"), nullptr, 0) : nullptr;
+        static const int dbg_env = getenv("SVLN_PF_DEBUG") ? atoi(getenv("SVLN_PF_DEBUG")) : 0;
+        p.debug = dbg_env;
+#ifdef SVLN_PF_INSTRUMENT   // build with SVLN_NVCC_EXTRA=-DSVLN_PF_INSTRUMENT: a device pointer in the environment is never
+                            // dereferenced by a production build
+        static long long* const trace_env = getenv("SVLN_PF_TRACE") ? (long long*)strtoull(getenv("SVLN_PF_TRACE"), nullptr, 0) : nullptr;
+        p.trace = trace_env;
+#else
+        p.trace = nullptr;
+#endif
         const int ns = n_seq - s0 < P3_MAX_SEQ ? n_seq - s0 : P3_MAX_SEQ;
         p.n_seq = ns;
         p.d_env = dev ? env_d + s0 : nullptr;

@@ -34,7 +34,10 @@
 // a barrier whose last arriver publishes a generation number to eight separate flag lines that the CTAs poll instead
 // of the arrival counter (3-6 % slower: one more L2 round trip per barrier than it saves in poll contention); dealing
 // rows round-robin (CTA c owns rows c, c + G, ...: the grid sweeps one contiguous band) instead of in contiguous
-// slices (no difference); 12 warps per CTA with a 16-slot ring (5 % slower: 168 registers per thread, more spills).
+// slices (no difference); 12 warps per CTA with a 16-slot ring (5 % slower: 168 registers per thread, more spills);
+// round 2: cp.async.bulk.prefetch.L2 of the bytes right behind the ring at every phase start (64 / 160 / 320 KB per CTA:
+// 4 / 6 / 9 % slower) and of the CTA's O slice + 0 / 256 / 512 KB of its gate/up slice from the idle warps during the
+// attention phase (1.5 / 3 / 8 % slower) - profiles/r2_decode_stack_experiments.md.
 // Rounding points are those of the unfused path (fused_ops.cu, kv_window.cu rope8, gemv.cu), i.e. HF's bf16
 // modules; accumulation order differs from cuBLAS, which the parity tolerance (1e-2 on logits) covers.
 #include <stdlib.h>
@@ -957,10 +960,13 @@ int svln_decode_stack_step(const svln_kv_arena* arena, const svln_decode_stack* 
     attr[0].val.cooperative = 1;
     cfg.attrs = attr;
     cfg.numAttrs = coop ? 1 : 0;
-    static size_t smem_set = 0;
-    if (smem > smem_set) {
+    static size_t smem_set[64] = {0};      // per device: function attributes do not carry over to another GPU
+    int dev_i = 0;
+    SVLN_CUDA(cudaGetDevice(&dev_i));
+    dev_i = dev_i < 0 || dev_i >= 64 ? 0 : dev_i;
+    if (smem > smem_set[dev_i]) {
         SVLN_CUDA(cudaFuncSetAttribute(decode_stack_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        smem_set = smem;
+        smem_set[dev_i] = smem;
     }
     SVLN_CUDA(cudaLaunchKernelEx(&cfg, decode_stack_kernel<1>, p));
     return check_launch("decode_stack_kernel");

@@ -17,38 +17,26 @@ __device__ __forceinline__ int64_t plane_offset(const svln_kv_arena& a, int env,
 // ------------------------------------------------------------------ fused RoPE + append
 // 8 threads per 128-wide head vector; thread j owns dims [8j,8j+8) and [64+8j,64+8j+8).
 // HF rounding points (apply_rotary_pos_emb in bf16): out = bf16(bf16(x*cos) + bf16(rot(x)*sin)).
+// Packed bf16x2 arithmetic: a product of two bf16 values is exact in fp32, so HMUL2.BF16 (one rounding) equals HF's
+// bf16(x * cos); the sum of two bf16 values rounded once equals the fp32 sum rounded to bf16 (no double-rounding case
+// exists for 8-bit significands).  The _rn intrinsics forbid contraction into an FMA, which would drop HF's
+// intermediate rounding.  6 packed instructions per 4 outputs instead of ~40 scalar ones: the kernel was issue-bound
+// (ncu round 1: DRAM 45 % while SM throughput 73 %).
 __device__ __forceinline__ void rope8(const int4& lo, const int4& hi, const int4& cos_lo, const int4& cos_hi,
                                       const int4& sin_lo, const int4& sin_hi, int4& out_lo, int4& out_hi) {
-    const uint32_t* l = reinterpret_cast<const uint32_t*>(&lo);
-    const uint32_t* h = reinterpret_cast<const uint32_t*>(&hi);
-    const uint32_t* cl = reinterpret_cast<const uint32_t*>(&cos_lo);
-    const uint32_t* ch = reinterpret_cast<const uint32_t*>(&cos_hi);
-    const uint32_t* sl = reinterpret_cast<const uint32_t*>(&sin_lo);
-    const uint32_t* sh = reinterpret_cast<const uint32_t*>(&sin_hi);
-    uint32_t* ol = reinterpret_cast<uint32_t*>(&out_lo);
-    uint32_t* oh = reinterpret_cast<uint32_t*>(&out_hi);
+    const __nv_bfloat162* l = reinterpret_cast<const __nv_bfloat162*>(&lo);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&hi);
+    const __nv_bfloat162* cl = reinterpret_cast<const __nv_bfloat162*>(&cos_lo);
+    const __nv_bfloat162* ch = reinterpret_cast<const __nv_bfloat162*>(&cos_hi);
+    const __nv_bfloat162* sl = reinterpret_cast<const __nv_bfloat162*>(&sin_lo);
+    const __nv_bfloat162* sh = reinterpret_cast<const __nv_bfloat162*>(&sin_hi);
+    __nv_bfloat162* ol = reinterpret_cast<__nv_bfloat162*>(&out_lo);
+    __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&out_hi);
 #pragma unroll
     for (int w = 0; w < 4; ++w) {
-        uint32_t rl = 0, rh = 0;
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-            const int sft = e * 16;
-            const float xl = bf16_bits_to_f32((l[w] >> sft) & 0xFFFFu);
-            const float xh = bf16_bits_to_f32((h[w] >> sft) & 0xFFFFu);
-            const float c_l = bf16_bits_to_f32((cl[w] >> sft) & 0xFFFFu);
-            const float c_h = bf16_bits_to_f32((ch[w] >> sft) & 0xFFFFu);
-            const float s_l = bf16_bits_to_f32((sl[w] >> sft) & 0xFFFFu);
-            const float s_h = bf16_bits_to_f32((sh[w] >> sft) & 0xFFFFu);
-            // lo: x_lo*cos_lo + (-x_hi)*sin_lo ; hi: x_hi*cos_hi + x_lo*sin_hi
-            const float a = round_bf16(__fmul_rn(xl, c_l));
-            const float b = round_bf16(__fmul_rn(-xh, s_l));
-            const float c = round_bf16(__fmul_rn(xh, c_h));
-            const float d = round_bf16(__fmul_rn(xl, s_h));
-            rl |= f32_to_bf16_bits(__fadd_rn(a, b)) << sft;
-            rh |= f32_to_bf16_bits(__fadd_rn(c, d)) << sft;
-        }
-        ol[w] = rl;
-        oh[w] = rh;
+        // lo: x_lo*cos_lo + (-x_hi)*sin_lo ; hi: x_hi*cos_hi + x_lo*sin_hi   (rotate_half(x) = (-x_hi, x_lo))
+        ol[w] = __hsub2_rn(__hmul2_rn(l[w], cl[w]), __hmul2_rn(h[w], sl[w]));
+        oh[w] = __hadd2_rn(__hmul2_rn(h[w], ch[w]), __hmul2_rn(l[w], sh[w]));
     }
 }
 

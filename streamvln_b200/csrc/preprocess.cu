@@ -66,6 +66,26 @@ resample_v_norm_kernel(const uint8_t* __restrict__ tmp, int H, int OW, int OH, c
     o[2 * plane] = __fmul_rn(__fsub_rn(__fmul_rn((float)clip8(a2), s), 0.5f), 2.0f);
 }
 
+// Depth frame: Habitat's [0,1] float depth -> metres on the out x out processor grid, as the reference's eval loop does
+// on the host (streamvln_eval.py:254-256 scale to metres and millimetres, :276 uint16 truncation, :126-135 Pillow NEAREST
+// squash + / 1000).  Pillow's nearest source index is (int)((i + 0.5) * in / out) in double arithmetic; the uint16 value
+// is divided by 1000 in double and rounded to float32 once, like numpy's uint16 / int -> float64 followed by .float().
+__global__ void __launch_bounds__(256)
+depth_nearest_kernel(const float* __restrict__ in, int H, int W, int OH, int OW, float span, float min_depth,
+                     float* __restrict__ out, int64_t total) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // over n*OH*OW
+    if (i >= total) return;
+    const int xo = (int)(i % OW);
+    const int yo = (int)((i / OW) % OH);
+    const int64_t n = i / ((int64_t)OW * OH);
+    const int ys = (int)(((double)yo + 0.5) * ((double)H / (double)OH));
+    const int xs = (int)(((double)xo + 0.5) * ((double)W / (double)OW));
+    const float d = in[(n * H + ys) * W + xs];
+    const float mm = __fmul_rn(__fadd_rn(__fmul_rn(d, span), min_depth), 1000.0f);   // float32, as numpy computes it
+    const unsigned short q = (unsigned short)(int)mm;                                 // .astype(np.uint16): truncation (depth >= 0)
+    out[i] = (float)((double)q / 1000.0);
+}
+
 }  // namespace svln
 
 using namespace svln;
@@ -95,6 +115,19 @@ int svln_preprocess_rgb(const uint8_t* rgb, int n, int H, int W, int out_h, int 
     resample_v_norm_kernel<<<(unsigned)((t2 + 255) / 256), 256, 0, st>>>((const uint8_t*)workspace, H, out_w, out_h, ymin, ycnt,
                                                                          ykk, yksize, out, t2);
     return check_launch("preprocess kernels");
+}
+
+int svln_preprocess_depth(const float* depth01, int n, int H, int W, int out_h, int out_w, float min_depth,
+                          float max_depth, float* out, svln_stream_t stream) {
+    SVLN_REQUIRE(n >= 0 && H > 0 && W > 0 && out_h > 0 && out_w > 0 && max_depth > min_depth && min_depth >= 0.f, SVLN_ERR_INVALID,
+                 "svln_preprocess_depth: bad arguments");
+    if (n == 0) return SVLN_OK;
+    SVLN_REQUIRE(depth01 && out, SVLN_ERR_INVALID, "svln_preprocess_depth: null pointer");
+    SVLN_REQUIRE(max_depth * 1000.f < 65536.f, SVLN_ERR_RANGE, "svln_preprocess_depth: max_depth %.1f m overflows the uint16 millimetres", max_depth);
+    const int64_t total = (int64_t)n * out_h * out_w;
+    depth_nearest_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(depth01, H, W, out_h, out_w,
+                                                                                           max_depth - min_depth, min_depth, out, total);
+    return check_launch("depth_nearest_kernel");
 }
 
 }  // extern "C"

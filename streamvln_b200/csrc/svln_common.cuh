@@ -12,6 +12,9 @@ namespace svln {
 void set_error(const char* fmt, ...);
 int check_launch(const char* what);
 int sm_count();
+// true the first time it is called for `*mask` on the CURRENT device: function attributes (opt-in shared memory) are
+// per device, so a per-process `static bool` would leave every device after the first at the 48 KB default
+bool first_use_on_device(unsigned long long* mask);
 
 #define SVLN_REQUIRE(cond, code, ...)      \
     do {                                   \

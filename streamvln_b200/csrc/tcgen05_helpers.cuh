@@ -116,13 +116,8 @@ __host__ __device__ constexpr uint32_t umma_idesc(int b_mn_major, uint32_t n = 1
 }
 
 
-// host side (attn_prefill.cu / attn_prefill2.cu)
+// host side (attn_prefill.cu: entry points + tensor-map cache; attn_prefill3.cu: the kernel and its launch)
 int get_kv_map(const svln_kv_arena* a, int box_rows, CUtensorMap* out);
-int prefill2_launch(const svln_kv_arena* arena, int layer, const void* q, int n_q_head, const int32_t* env_h,
-                    const int32_t* q_start_h, const int32_t* n_q_h, const int32_t* kv_len_h, const int32_t* env_d,
-                    const int32_t* q_start_d, const int32_t* n_q_d, const int32_t* kv_len_d, int n_seq, float scale,
-                    void* out, svln_stream_t stream, const char* who);
-
 int prefill3_launch(const svln_kv_arena* arena, int layer, const void* q, int n_q_head, const int32_t* env_h,
                     const int32_t* q_start_h, const int32_t* n_q_h, const int32_t* kv_len_h, const int32_t* env_d,
                     const int32_t* q_start_d, const int32_t* n_q_d, const int32_t* kv_len_d, int n_seq, float scale,

@@ -454,11 +454,10 @@ static int keep_latest_impl(const int64_t* key, const int32_t* t, int64_t n_toke
     const uint32_t cap = table_cap(max_seg_tokens);
     if (max_seg_tokens <= SMEM_DEDUP_MAX_TOKENS) {
         const size_t smem = (size_t)cap * 12;
-        static bool attr_set = false;
-        if (!attr_set) {
+        static unsigned long long attr_set = 0;
+        if (first_use_on_device(&attr_set)) {
             SVLN_CUDA(cudaFuncSetAttribute(dedup_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)SMEM_DEDUP_MAX_BYTES));
-            attr_set = true;
         }
         dedup_smem_kernel<<<(unsigned)n_segments, SMEM_DEDUP_THREADS, smem, st>>>(
             key, t, seg_off, uniform, n_tokens, cap - 1, invalid_policy, mask_out);

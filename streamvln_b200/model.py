@@ -114,6 +114,70 @@ class StreamVLNForCausalLM:
         self.tokens_per_frame = config.vision.pooled_per_side ** 2
         self.reset(n_env)
 
+    # ------------------------------------------------------------------ checkpoints
+    @classmethod
+    def from_pretrained(cls, path, device="cuda", n_env: int = 1, mode: str = "reference", **overrides) -> "StreamVLNForCausalLM":
+        """Load a StreamVLN / LLaVA-Video-Qwen2 checkpoint directory (HF layout: config.json + *.safetensors with the
+        names `model.*`, `model.vision_tower.vision_tower.*`, `model.mm_projector.*`, `lm_head.*`), the counterpart of
+        `StreamVLNForCausalLM.from_pretrained(model_path, torch_dtype=bfloat16, ...)` at streamvln_agent.py:281-293 /
+        streamvln_eval.py:521-533.  `overrides` set StreamVLNConfig fields (window_turns, voxel_size, ...)."""
+        import json
+        from pathlib import Path
+
+        from safetensors import safe_open
+
+        path = Path(path)
+        hc = json.loads((path / "config.json").read_text())
+        llm = Qwen2Config(hidden_size=hc["hidden_size"], num_hidden_layers=hc["num_hidden_layers"],
+                          num_attention_heads=hc["num_attention_heads"], num_key_value_heads=hc.get("num_key_value_heads", hc["num_attention_heads"]),
+                          head_dim=hc.get("head_dim") or hc["hidden_size"] // hc["num_attention_heads"], intermediate_size=hc["intermediate_size"],
+                          vocab_size=hc["vocab_size"], rope_theta=float(hc.get("rope_theta", 1e6)), rms_norm_eps=float(hc.get("rms_norm_eps", 1e-6)),
+                          max_position_embeddings=int(hc.get("tokenizer_model_max_length") or hc.get("svln_arena_rows") or 4096))
+        vc = hc.get("svln_vision") or {}
+        vision_cfg = VisionConfig(out_dim=llm.hidden_size, pool_mode=hc.get("mm_spatial_pool_mode", "bilinear"),
+                                  pool_stride=int(hc.get("mm_spatial_pool_stride", 2)), **vc)
+        eos = hc.get("eos_token_id")
+        cfg = StreamVLNConfig(llm=llm, vision=vision_cfg, num_history=hc.get("num_history", 8), mode=mode,
+                              eos_token_id=eos[0] if isinstance(eos, list) else eos)
+        for k, v in overrides.items():
+            if not hasattr(cfg, k):
+                raise TypeError(f"unknown StreamVLNConfig field {k!r}")
+            setattr(cfg, k, v)
+        sd: Dict[str, torch.Tensor] = {}
+        shards = sorted(path.glob("*.safetensors"))
+        if not shards:
+            raise FileNotFoundError(f"no *.safetensors under {path}")
+        for f in shards:
+            with safe_open(str(f), framework="pt", device="cpu") as st:
+                for k in st.keys():
+                    sd[k] = st.get_tensor(k)
+        weights = Qwen2Weights.from_state_dict(llm, sd, device)
+        vision = VisionFrontEnd(vision_cfg, device)
+        vision.load_hf_state_dict(sd)
+        return cls(cfg, weights=weights, vision=vision, n_env=n_env, device=device)
+
+    def save_pretrained(self, path) -> None:
+        """Write config.json + model.safetensors in the layout `from_pretrained` (and HF) reads."""
+        import json
+        from pathlib import Path
+
+        from safetensors.torch import save_file
+
+        path = Path(path)
+        path.mkdir(parents=True, exist_ok=True)
+        c, v = self.config.llm, self.config.vision
+        hc = dict(architectures=["StreamVLNForCausalLM"], model_type="llava_qwen", hidden_size=c.hidden_size, num_hidden_layers=c.num_hidden_layers,
+                  num_attention_heads=c.num_attention_heads, num_key_value_heads=c.num_key_value_heads, head_dim=c.head_dim,
+                  intermediate_size=c.intermediate_size, vocab_size=c.vocab_size, rope_theta=c.rope_theta, rms_norm_eps=c.rms_norm_eps,
+                  svln_arena_rows=c.max_position_embeddings, num_history=self.model.num_history, eos_token_id=self.config.eos_token_id,
+                  mm_spatial_pool_mode=v.pool_mode, mm_spatial_pool_stride=v.pool_stride, mm_projector_type="mlp2x_gelu",
+                  svln_vision=dict(hidden_size=v.hidden_size, intermediate_size=v.intermediate_size, num_layers=v.num_layers, num_heads=v.num_heads,
+                                   image_size=v.image_size, patch_size=v.patch_size, layer_norm_eps=v.layer_norm_eps))
+        (path / "config.json").write_text(json.dumps(hc, indent=1))
+        sd = {k: t.cpu().contiguous() for k, t in self.weights.to_hf_state_dict().items()}
+        sd.update({k: t.cpu().contiguous() for k, t in self.vision.to_hf_state_dict().items()})
+        save_file(sd, str(path / "model.safetensors"))
+
     # ------------------------------------------------------------------ reference object surface
     def get_model(self):
         return self.model

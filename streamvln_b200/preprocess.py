@@ -76,3 +76,21 @@ class GpuImageProcessor:
                                            ptr(yl), ptr(yn), ptr(yk), yks, ptr(self._ws), self._ws.numel(), ptr(out),
                                            cur_stream()))
         return out
+
+
+class GpuDepthProcessor:
+    """Habitat [0,1] depth [n,H,W] (device float32) -> metres on the 384x384 grid through svln_preprocess_depth, bit-exact
+    with the reference's host path (streamvln_eval.py:126-135,254-256,276; host restatement: synth.preprocess_depth)."""
+
+    def __init__(self, device, size: int = 384, min_depth: float = 0.0, max_depth: float = 10.0):
+        self.lib = _lib.load()
+        self.device, self.size, self.min_depth, self.max_depth = torch.device(device), size, min_depth, max_depth
+
+    def __call__(self, depth01: torch.Tensor) -> torch.Tensor:
+        d = depth01.to(self.device, torch.float32).contiguous()
+        d = d.reshape(-1, d.shape[-2], d.shape[-1]) if d.dim() != 3 else d
+        n, H, W = d.shape
+        out = torch.empty(n, self.size, self.size, dtype=torch.float32, device=self.device)
+        check(self.lib.svln_preprocess_depth(ptr(d), n, H, W, self.size, self.size, self.min_depth, self.max_depth, ptr(out),
+                                             cur_stream()))
+        return out

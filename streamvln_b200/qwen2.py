@@ -593,6 +593,7 @@ class _PrefillGraph:
         self.h_in = torch.zeros(n_tok, D, dtype=torch.bfloat16, device=eng.device)
         self.meta = torch.zeros(2 * n_tok + 5 * n_seq, dtype=torch.int32, device=eng.device)
         self.meta_host = torch.zeros(2 * n_tok + 5 * n_seq, dtype=torch.int32).pin_memory()
+        self._meta_free: Optional[torch.cuda.Event] = None
         before = eng.launches
         self.graph = torch.cuda.CUDAGraph()
         # the shapes were just run eagerly by forward() (cuBLAS / allocator are warm); capture executes nothing
@@ -602,8 +603,12 @@ class _PrefillGraph:
         eng.launches = before
 
     def run(self, h: torch.Tensor, packed: torch.Tensor) -> torch.Tensor:
+        if self._meta_free is not None:
+            self._meta_free.synchronize()   # the previous replay's async H2D has left the pinned staging buffer
         self.meta_host.copy_(packed)
         self.meta.copy_(self.meta_host, non_blocking=True)
+        self._meta_free = torch.cuda.Event()
+        self._meta_free.record()
         self.h_in.copy_(h)
         self.graph.replay()
         self.eng.launches += self.launches_per_replay

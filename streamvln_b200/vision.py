@@ -131,6 +131,25 @@ class VisionFrontEnd(torch.nn.Module):
             self.proj_w2.copy_(sd[projector_prefix + "2.weight"].to(dev, dt)); self.proj_b2.copy_(sd[projector_prefix + "2.bias"].to(dev, dt))
         self._graphs.clear()
 
+    def to_hf_state_dict(self, prefix: str = "model.vision_tower.vision_tower.", projector_prefix: str = "model.mm_projector.") -> Dict[str, torch.Tensor]:
+        """Inverse of load_hf_state_dict (checkpoint round trips in the tests / save_pretrained)."""
+        cfg = self.cfg
+        D, ps = cfg.hidden_size, cfg.patch_size
+        sd = {"embeddings.patch_embedding.weight": self.patch_w.reshape(D, 3, ps, ps), "embeddings.patch_embedding.bias": self.patch_b,
+              "embeddings.position_embedding.weight": self.pos}
+        for i in range(cfg.num_layers):
+            L, e = self._layer(i), f"encoder.layers.{i}."
+            for j, n in enumerate("qkv"):
+                sd[e + f"self_attn.{n}_proj.weight"] = L["wqkv"][j * D:(j + 1) * D]
+                sd[e + f"self_attn.{n}_proj.bias"] = L["bqkv"][j * D:(j + 1) * D]
+            sd.update({e + "layer_norm1.weight": L["ln1_w"], e + "layer_norm1.bias": L["ln1_b"], e + "self_attn.out_proj.weight": L["wo"],
+                       e + "self_attn.out_proj.bias": L["bo"], e + "layer_norm2.weight": L["ln2_w"], e + "layer_norm2.bias": L["ln2_b"],
+                       e + "mlp.fc1.weight": L["w1"], e + "mlp.fc1.bias": L["b1"], e + "mlp.fc2.weight": L["w2"], e + "mlp.fc2.bias": L["b2"]})
+        out = {prefix + "vision_model." + k: v.detach().contiguous() for k, v in sd.items()}
+        out.update({projector_prefix + "0.weight": self.proj_w1.detach(), projector_prefix + "0.bias": self.proj_b1.detach(),
+                    projector_prefix + "2.weight": self.proj_w2.detach(), projector_prefix + "2.bias": self.proj_b2.detach()})
+        return out
+
     # attribute access used by the reference's call sites (streamvln_agent.py:43)
     @property
     def num_patches_per_side(self) -> int:

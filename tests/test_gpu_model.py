@@ -332,3 +332,45 @@ def test_pool_bilinear_kernel_matches_reference_pool(svln_lib, cuda):
         bound = torch.maximum(want.float().abs(), got.float().abs()) * 2.0 ** -7   # one ulp of the larger binade
         # + an absolute floor for results that are tiny by cancellation (fp32 rounding of operands of magnitude ~10)
         assert bool((diff <= bound * 1.001 + 1e-5).all()), (side, dim, float(diff.max()))
+
+
+def test_gpu_depth_processor_matches_reference_host_path(svln_lib, cuda):
+    """svln_preprocess_depth == the Habitat evaluator's host depth path, bit for bit: against the golden fixture produced
+    by the reference's own preprocess_depth_image (tests/golden/ref_geometry.npz) and against synth.preprocess_depth on
+    other shapes."""
+    from pathlib import Path
+    from streamvln_b200 import synth
+    from streamvln_b200.preprocess import GpuDepthProcessor
+
+    z = np.load(Path(__file__).resolve().parent / "golden" / "ref_geometry.npz")
+    proc = GpuDepthProcessor(cuda)
+    got = proc(torch.from_numpy(z["depth01"]).to(cuda))[0].cpu().numpy()
+    assert np.array_equal(got, z["depth384"].astype(np.float32))
+    rng = np.random.default_rng(3)
+    for h, w in ((480, 640), (256, 256), (97, 131)):
+        d = rng.uniform(0, 1, size=(2, h, w)).astype(np.float32)
+        d[0, : h // 3] = 0.0
+        got = proc(torch.from_numpy(d).to(cuda)).cpu().numpy()
+        for i in range(2):
+            assert np.array_equal(got[i], synth.preprocess_depth(d[i])), (h, w, i)
+
+
+def test_from_pretrained_round_trip(tiny, cuda, tmp_path):
+    """save_pretrained -> from_pretrained (HF layout: config.json + model.safetensors with the reference's parameter names,
+    streamvln_agent.py:281-293) reproduces the model bit for bit: identical weights, identical greedy ids on a turn."""
+    from streamvln_b200.model import StreamVLNForCausalLM
+
+    m, _ = tiny
+    m.save_pretrained(tmp_path / "ckpt")
+    m2 = StreamVLNForCausalLM.from_pretrained(tmp_path / "ckpt", device=cuda, n_env=1)
+    assert m2.config.llm == m.config.llm and m2.config.vision == m.config.vision
+    for a, b in zip(m.weights.layers, m2.weights.layers):
+        assert all(torch.equal(a[k], b[k]) for k in a)
+    assert torch.equal(m.weights.lm_head, m2.weights.lm_head) and torch.equal(m.weights.final_norm, m2.weights.final_norm)
+    assert all(torch.equal(p, q) for p, q in zip(m.vision.parameters(), m2.vision.parameters()))
+    frames = torch.randn(1, 1, 3, 384, 384, generator=torch.Generator().manual_seed(9)) * 0.5
+    ids = torch.tensor([[7, 8, glue.IMAGE_TOKEN_INDEX, 10, 11]])
+    m.reset(2)
+    r1 = m.generate(inputs=ids, images=frames, env_id=0, time_ids=[[0]], max_new_tokens=4, past_key_values=None)
+    r2 = m2.generate(inputs=ids, images=frames, env_id=0, time_ids=[[0]], max_new_tokens=4, past_key_values=None)
+    assert r1.sequences.tolist() == r2.sequences.tolist()

@@ -35,3 +35,14 @@ def test_tower_matches_transformers_siglip():
     want_feat, _ = glue.encode_rgbd(want, proj, 8, [0])
     assert torch.allclose(v.project_pool(got), want_feat, atol=2e-5, rtol=1e-4)
     assert v(x).shape == (2, 196, 96)
+
+
+def test_vision_state_dict_round_trip():
+    """to_hf_state_dict is the inverse of load_hf_state_dict (what save_pretrained / from_pretrained rely on)."""
+    cfg = VisionConfig(hidden_size=64, intermediate_size=128, num_layers=2, num_heads=4, out_dim=96)
+    a = VisionFrontEnd(cfg, device="cpu", dtype=torch.float32, seed=3)
+    b = VisionFrontEnd(cfg, device="cpu", dtype=torch.float32, seed=4)
+    b.load_hf_state_dict(a.to_hf_state_dict())
+    assert all(torch.equal(p, q) for p, q in zip(a.parameters(), b.parameters()))
+    x = torch.randn(1, 3, 384, 384, generator=torch.Generator().manual_seed(0))
+    assert torch.equal(a(x), b(x))
