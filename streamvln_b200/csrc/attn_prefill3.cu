@@ -792,7 +792,11 @@ attn_prefill3p_kernel(const __grid_constant__ CUtensorMap kv_map, const __grid_c
     }
 }
 
-// merge the split-KV partials of one (M tile, kv head): one warp per row, lanes over dims (4 floats each)
+// merge the split-KV partials of one (M tile, kv head): one warp per row, lanes over dims (4 floats each).  The grid's
+// z dimension cuts the tile into 32-row slabs and every warp issues the loads of its 4 rows x all splits before it uses
+// any of them: the first version walked 16 rows per warp one dependent L2 round trip after the other and took ~30 us,
+// which is why split-KV measured SLOWER than the 48-CTA grid in round 1 (53 vs 40 us per layer).
+constexpr int P3C_ROWS = 32, P3C_MAX_SPLITS = 4;
 __global__ void __launch_bounds__(256)
 attn_prefill3_combine_kernel(const __grid_constant__ Prefill3Params p) {
     const int gtile = blockIdx.x, kvh = blockIdx.y;
@@ -805,20 +809,37 @@ attn_prefill3_combine_kernel(const __grid_constant__ Prefill3Params p) {
     const int rows_total = nq * g;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t slot0 = ((int64_t)gtile * gridDim.y + kvh) * p.n_splits;
-    for (int r = warp; r < P3_BM; r += 8) {
+    constexpr int RPW = P3C_ROWS / 8;
+    float ms[RPW][P3C_MAX_SPLITS], ls[RPW][P3C_MAX_SPLITS];
+    float4 o[RPW][P3C_MAX_SPLITS];
+#pragma unroll
+    for (int i = 0; i < RPW; ++i) {
+        const int r = blockIdx.z * P3C_ROWS + i * 8 + warp;
+#pragma unroll
+        for (int s_ = 0; s_ < P3C_MAX_SPLITS; ++s_) {
+            const bool ok = s_ < p.n_splits && mtile * P3_BM + r < rows_total;
+            const int64_t at = (slot0 + (ok ? s_ : 0)) * P3_BM + r;
+            ms[i][s_] = ok ? p.part_ml[at * 2] : -INFINITY;
+            ls[i][s_] = ok ? p.part_ml[at * 2 + 1] : 0.f;
+            o[i][s_] = ok ? *reinterpret_cast<const float4*>(p.part_o + at * P3_HD + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < RPW; ++i) {
+        const int r = blockIdx.z * P3C_ROWS + i * 8 + warp;
         const int R = mtile * P3_BM + r;
-        if (R >= rows_total) break;
+        if (R >= rows_total) continue;
         float m = -INFINITY;
-        for (int s = 0; s < p.n_splits; ++s) m = fmaxf(m, p.part_ml[((slot0 + s) * P3_BM + r) * 2]);
+#pragma unroll
+        for (int s_ = 0; s_ < P3C_MAX_SPLITS; ++s_) m = fmaxf(m, ms[i][s_]);
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
         float l = 0.f;
-        for (int s = 0; s < p.n_splits; ++s) {
-            const float ms = p.part_ml[((slot0 + s) * P3_BM + r) * 2];
-            if (ms == -INFINITY) continue;
-            const float w = exp2f(ms - m);
-            l += p.part_ml[((slot0 + s) * P3_BM + r) * 2 + 1] * w;
-            const float4 o = *reinterpret_cast<const float4*>(p.part_o + ((slot0 + s) * P3_BM + r) * P3_HD + lane * 4);
-            acc.x += o.x * w; acc.y += o.y * w; acc.z += o.z * w; acc.w += o.w * w;
+#pragma unroll
+        for (int s_ = 0; s_ < P3C_MAX_SPLITS; ++s_) {        // fixed split order: deterministic
+            if (ms[i][s_] == -INFINITY) continue;
+            const float w = exp2f(ms[i][s_] - m);
+            l += ls[i][s_] * w;
+            acc.x += o[i][s_].x * w; acc.y += o[i][s_].y * w; acc.z += o[i][s_].z * w; acc.w += o[i][s_].w * w;
         }
         const float inv_l = l > 0.f ? 1.0f / l : 0.f;
         const int tq = R / g, hg = R - tq * g;
@@ -900,13 +921,14 @@ int prefill3_launch(const svln_kv_arena* arena, int layer, const void* q, int n_
         // split the key range when the grid cannot fill the GPU (single-episode turns: 12 M tiles x 4 kv heads)
         const int ctas = tiles * arena->n_kv_head;
         int n_splits = 1;
-        // measured on B200 (single-episode turn, 48 CTAs): splitting 2-3 ways does not pay - the fixed per-CTA cost
-        // (TMEM alloc, Q -> TMEM, pipeline fill) plus the combine pass outweighs the shorter key loops - so it is
-        // opt-in (SVLN_PF_SPLITS=n) rather than the default
-        static const int max_splits = getenv("SVLN_PF_SPLITS") ? atoi(getenv("SVLN_PF_SPLITS")) : 1;
+        // measured on B200 (single-episode steady turn, 217 q x 7 heads over 3000 keys = 48 CTAs, L2 flushed): 1 / 2 / 3 / 4
+        // splits = 40.0 / 33.8 / 29.6 / 29.7 us per layer (round 2, after the combine kernel stopped serialising its L2
+        // round trips); SVLN_PF_SPLITS=1 turns it off
+        static const int max_splits = getenv("SVLN_PF_SPLITS") ? atoi(getenv("SVLN_PF_SPLITS")) : 3;
         if (!use_cluster && workspace && ctas * 2 <= sm_count() && max_splits > 1) {
             n_splits = sm_count() / ctas;   // one wave: never more CTAs than SMs (each CTA owns a whole SM)
             if (n_splits > max_splits) n_splits = max_splits;
+            if (n_splits > P3C_MAX_SPLITS) n_splits = P3C_MAX_SPLITS;
             while (n_splits > 1 && prefill3_workspace_bytes((int64_t)ctas * n_splits) > workspace_bytes) --n_splits;
         }
         p.n_splits = n_splits;
@@ -935,7 +957,7 @@ int prefill3_launch(const svln_kv_arena* arena, int layer, const void* q, int n_
             attn_prefill3_kernel<false><<<grid, P3_THREADS, P3_SMEM, (cudaStream_t)stream>>>(map, p);
         }
         if (n_splits > 1) {
-            dim3 cgrid(tiles, arena->n_kv_head);
+            dim3 cgrid(tiles, arena->n_kv_head, P3_BM / P3C_ROWS);
             attn_prefill3_combine_kernel<<<cgrid, 256, 0, (cudaStream_t)stream>>>(p);
         }
         rc = check_launch("attn_prefill3_kernel");
