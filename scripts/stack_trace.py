@@ -62,3 +62,24 @@ print(f"all {G} CTAs, layer {L // 2}, ns since the first CTA passed the layer's 
 for k in sorted(names):
     v = gt[:, k] - t0
     print(f"  {names[k]:22s} {v.min():8.0f} {v.mean():8.0f} {v.max():8.0f}   (argmax CTA {int(v.argmax())})")
+
+# ---- per-CTA streaming time of the gate/up phase (slots 9 -> 10) and its persistence across steps
+def gu_durations():
+    n = eng.lib.svln_decode_stack_trace(buf.ctypes.data_as(C.c_void_p), buf.size)
+    g = buf[nt + 8:].reshape(160, 16).astype(np.float64)[:G]
+    return g[:, 10] - g[:, 9], g[:, 13] - g[:, 12]
+runs = []
+for _ in range(3):
+    for _ in range(2):
+        tok = runner.step(tok)
+    torch.cuda.synchronize()
+    runs.append(gu_durations())
+gu = np.stack([r[0] for r in runs]); dn = np.stack([r[1] for r in runs])
+print("gate/up main-loop ns per CTA: mean %.0f  min %.0f  max %.0f  std %.0f" % (gu.mean(), gu.min(), gu.max(), gu.std()))
+print("correlation of per-CTA gate/up times between steps: %.3f %.3f; gate/up vs down: %.3f" %
+      (np.corrcoef(gu[0], gu[1])[0, 1], np.corrcoef(gu[1], gu[2])[0, 1], np.corrcoef(gu.mean(0), dn.mean(0))[0, 1]))
+order = np.argsort(gu.mean(0))
+print("slowest CTAs (mean over 3 steps):", [(int(c), int(gu.mean(0)[c])) for c in order[-8:]])
+print("fastest CTAs:", [(int(c), int(gu.mean(0)[c])) for c in order[:8]])
+rel = gu.mean(0) / gu.mean()
+print("relative time quantiles 5/25/50/75/95 %%: " + " ".join("%.3f" % q for q in np.quantile(rel, [0.05, 0.25, 0.5, 0.75, 0.95])))
