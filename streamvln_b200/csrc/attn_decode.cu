@@ -6,6 +6,8 @@
 // K/V tiles stream through a 3-stage cp.async ring with a 128-byte XOR swizzle; the scalar
 // fp32 pipe could not keep up with HBM for g = 7 (3.5 FMA per byte), so the dot products run
 // on the legacy tensor path (HMMA) — the tcgen05 path is reserved for the dense prefill.
+#include <stdlib.h>
+
 #include "attn_decode_body.cuh"
 
 namespace svln {
@@ -113,6 +115,16 @@ int svln_attn_decode(const svln_kv_arena* arena, int layer, const void* q, int n
     int tiles_per_split = (int)((tiles + want - 1) / want);
     if (tiles_per_split < 4) tiles_per_split = tiles < 4 ? tiles : 4;
     p.n_splits = (tiles + tiles_per_split - 1) / tiles_per_split;
+    // With >= 1.5 CTAs per SM before any split (64 streams x 4 kv heads = 256) one split per (stream, kv head) is best:
+    // it writes the final rows itself, so the partials and the combine launch disappear (measured at 64 x 3000 keys,
+    // L2 flushed: 1 / 2 / 3 / 4 / 6 splits + combine = 88.4 / 89.0 / 91.6 / 92.6 / 95.1 us; 1 split without combine: see
+    // profiles/).  SVLN_AD_SPLITS overrides (experiments).
+    static const int splits_env = getenv("SVLN_AD_SPLITS") ? atoi(getenv("SVLN_AD_SPLITS")) : 0;
+    const int force = splits_env > 0 ? splits_env : (2 * base_ctas >= 3ll * sm_count() ? 1 : 0);
+    if (force > 0) {
+        tiles_per_split = (tiles + force - 1) / force;
+        p.n_splits = (tiles + tiles_per_split - 1) / tiles_per_split;
+    }
     p.split_keys = tiles_per_split * DT;
     p.scale_log2 = scale * 1.4426950408889634f;
     const size_t slots = (size_t)base_ctas * p.n_splits;
@@ -130,8 +142,10 @@ int svln_attn_decode(const svln_kv_arena* arena, int layer, const void* q, int n
     }
     dim3 grid(p.n_splits, arena->n_kv_head, (unsigned)groups);
     attn_decode_kernel<<<grid, DWARPS * 32, DEC_SMEM, (cudaStream_t)stream>>>(p);
-    dim3 cgrid((unsigned)groups, arena->n_kv_head, DROWS);
-    attn_decode_combine_kernel<<<cgrid, HD, 0, (cudaStream_t)stream>>>(p);
+    if (p.n_splits > 1) {
+        dim3 cgrid((unsigned)groups, arena->n_kv_head, DROWS);
+        attn_decode_combine_kernel<<<cgrid, HD, 0, (cudaStream_t)stream>>>(p);
+    }
     return check_launch("attn_decode kernels");
 }
 

@@ -114,6 +114,11 @@ __device__ __forceinline__ void attn_decode_body(const DecodeParams& p, int spli
 
     if (MODE == 1 && k_begin >= k_end) return;
     if (k_begin >= k_end) {  // empty split: neutral partial
+        if (p.n_splits == 1) {
+            for (int r = 0; r < rows_valid; ++r)
+                p.out[((int64_t)(qs + tok0 + r / g) * p.n_q_head + kvh * g + r % g) * HD + tid] = __float2bfloat16_rn(0.f);
+            return;
+        }
         if (tid < DROWS) {
             p.part_m[slot * DROWS + tid] = -INFINITY;
             p.part_l[slot * DROWS + tid] = 0.f;
@@ -304,11 +309,30 @@ __device__ __forceinline__ void attn_decode_body(const DecodeParams& p, int spli
         if (w == 0 && r < rows_valid) p.part_m[slot * DROWS + r] = m;
     }
     group_sync<BAR_ID>();
+    float* s_lrow = s_f + DWARPS * DROWS;                         // [16]
     if (tid < rows_valid) {
         float l = 0.f;
 #pragma unroll
         for (int w = 0; w < DWARPS; ++w) l += s_l[w * DROWS + tid] * s_f[w * DROWS + tid];
-        p.part_l[slot * DROWS + tid] = l;
+        if (p.n_splits == 1) s_lrow[tid] = l;
+        else p.part_l[slot * DROWS + tid] = l;
+    }
+    if (p.n_splits == 1) {
+        // a single split owns the whole key range: normalise and store the final rows here (same arithmetic as
+        // attn_decode_combine_kernel with one split of weight 1), no partials, no second kernel
+        group_sync<BAR_ID>();
+#pragma unroll
+        for (int r = 0; r < DROWS; ++r) {
+            if (r < rows_valid) {
+                float acc = 0.f;
+#pragma unroll
+                for (int w = 0; w < DWARPS; ++w) acc += s_o[(w * DROWS + r) * HD + tid] * s_f[w * DROWS + r];
+                const float l = s_lrow[r];
+                const int tq = tok0 + r / g, hq = kvh * g + r % g;
+                p.out[((int64_t)(qs + tq) * p.n_q_head + hq) * HD + tid] = __float2bfloat16_rn(l > 0.f ? acc / l : 0.f);
+            }
+        }
+        return;
     }
     float* po = p.part_o + (slot * DROWS) * HD + tid;
 #pragma unroll
