@@ -153,6 +153,10 @@ __global__ void __launch_bounds__(SMEM_DEDUP_THREADS, 1)
 dedup_smem_kernel(const int64_t* __restrict__ key, const int32_t* __restrict__ t,
                   const int64_t* __restrict__ seg_off, int64_t uniform, int64_t n_tokens,
                   uint32_t cap_mask, int invalid_policy, uint8_t* __restrict__ mask) {
+    // gridDim.y CTAs share a segment by KEY: CTA y owns the voxels whose hash falls in its partition (every CTA scans the
+    // whole segment, inserts and resolves only its own keys), so the winner of a voxel is still decided inside one CTA
+    // and the result does not depend on the partition count.  64 segments used to mean 64 busy SMs of 148.
+    const uint32_t n_part = gridDim.y, my_part = blockIdx.y;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const uint32_t cap = cap_mask + 1;
     unsigned long long* skey = reinterpret_cast<unsigned long long*>(smem_raw);
@@ -172,17 +176,46 @@ dedup_smem_kernel(const int64_t* __restrict__ key, const int32_t* __restrict__ t
         skey[s] = 0xFFFFFFFFFFFFFFFFull;
         sbest[s] = 0xFFFFFFFFu;
     }
+    // Frame-time range of the segment.  When it fits 19 bits (always, for step counters) the winner of a voxel is ONE
+    // shared-memory atomicMin on the packed word ((t_max - t) << 13 | index): largest t first, lowest index on ties.
+    // Round 1 kept only the index and re-read t[current best] from global memory inside a CAS loop - a dependent L2
+    // round trip per contended insert, which is what made this stage latency-bound.  Wider ranges take that path still.
+    __shared__ int s_tmin, s_tmax;
+    if (threadIdx.x == 0) { s_tmin = 0x7FFFFFFF; s_tmax = (int)0x80000000; }
     __syncthreads();
+    {
+        int lo = 0x7FFFFFFF, hi = (int)0x80000000;
+        for (int i = threadIdx.x; i < seg_n; i += blockDim.x) {
+            const int v = tt[i];
+            lo = min(lo, v);
+            hi = max(hi, v);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+            hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+        }
+        if ((threadIdx.x & 31) == 0 && seg_n > 0) { atomicMin(&s_tmin, lo); atomicMax(&s_tmax, hi); }
+    }
+    __syncthreads();
+    const int tmax = s_tmax;
+    const bool packed = seg_n <= 8192 && (int64_t)tmax - (int64_t)s_tmin < (1 << 19);
     for (int i = threadIdx.x; i < seg_n; i += blockDim.x) {
         const int64_t k = key[seg_start + i];
         if (k < 0) continue;
+        const uint64_t hsh = mix64((uint64_t)k);
+        if ((uint32_t)(hsh >> 40) % n_part != my_part) continue;
         const int32_t ti = tt[i];
-        uint32_t slot = (uint32_t)mix64((uint64_t)k) & cap_mask;
+        uint32_t slot = (uint32_t)hsh & cap_mask;
         while (true) {
             const unsigned long long prev =
                 atomicCAS(&skey[slot], 0xFFFFFFFFFFFFFFFFull, (unsigned long long)k);
             if (prev == 0xFFFFFFFFFFFFFFFFull || prev == (unsigned long long)k) break;
             slot = (slot + 1) & cap_mask;
+        }
+        if (packed) {
+            atomicMin(&sbest[slot], ((uint32_t)(tmax - ti) << 13) | (uint32_t)i);
+            continue;
         }
         uint32_t cur = sbest[slot];
         while (true) {
@@ -202,11 +235,15 @@ dedup_smem_kernel(const int64_t* __restrict__ key, const int32_t* __restrict__ t
         const int64_t k = key[seg_start + i];
         uint8_t m;
         if (k < 0) {
+            if (my_part != 0) continue;
             m = invalid_policy == SVLN_INVALID_KEEP ? 1 : 0;
         } else {
-            uint32_t slot = (uint32_t)mix64((uint64_t)k) & cap_mask;
+            const uint64_t hsh = mix64((uint64_t)k);
+            if ((uint32_t)(hsh >> 40) % n_part != my_part) continue;
+            uint32_t slot = (uint32_t)hsh & cap_mask;
             while (skey[slot] != (unsigned long long)k) slot = (slot + 1) & cap_mask;
-            m = sbest[slot] == (uint32_t)i ? 1 : 0;
+            const uint32_t best = sbest[slot];
+            m = (packed ? (best & 0x1FFFu) : best) == (uint32_t)i ? 1 : 0;
         }
         mask[seg_start + i] = m;
     }
@@ -459,7 +496,10 @@ static int keep_latest_impl(const int64_t* key, const int32_t* t, int64_t n_toke
             SVLN_CUDA(cudaFuncSetAttribute(dedup_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)SMEM_DEDUP_MAX_BYTES));
         }
-        dedup_smem_kernel<<<(unsigned)n_segments, SMEM_DEDUP_THREADS, smem, st>>>(
+        // one CTA per SM (192 KB of shared memory each): spread a segment over as many CTAs as there are idle SMs
+        int n_part = (int)(sm_count() / (n_segments > 0 ? n_segments : 1));
+        n_part = n_part < 1 ? 1 : (n_part > 8 ? 8 : n_part);
+        dedup_smem_kernel<<<dim3((unsigned)n_segments, (unsigned)n_part), SMEM_DEDUP_THREADS, smem, st>>>(
             key, t, seg_off, uniform, n_tokens, cap - 1, invalid_policy, mask_out);
         return check_launch("dedup_smem_kernel");
     }
