@@ -76,11 +76,12 @@ def stack_traffic():
 class ClockSampler:
     """SM clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe).  NVML is polled from a
     thread of this process (nvidia_ml_py): spawning `nvidia-smi -lms` at the start of the timed region and its
-    periodic driver queries cost the first timed turns 3-12 ms each (measured); nvidia-smi is the fallback."""
+    periodic driver queries cost the first timed turns 3-12 ms each (measured); nvidia-smi is the fallback.  The timed
+    region is several seconds long, so a sample every 0.25 s is plenty and keeps the driver lock out of the way."""
 
     _BITS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
-    def __init__(self, gpu_index: int, period_s: float = 0.05):
+    def __init__(self, gpu_index: int, period_s: float = 0.25):
         self.idx, self.period = gpu_index, period_s
         self.sm, self.mx, self.reasons = [], [], set()
         self.thread = self.proc = self.nvml = self.handle = None
@@ -183,7 +184,14 @@ def build_agent(device, mode: str, share=None):
 def run_turns(agent, n_turns: int, frames_host, frames_dev, resident: bool, geom=None):
     """n_turns model turns = 4*n_turns env steps through VLNEvaluator.step (the call a user makes)."""
     h2d = d2h = 0
-    for _ in range(n_turns):
+    verbose = os.environ.get("SVLN_BENCH_VERBOSE") == "1"
+    marks = []
+    for ti in range(n_turns):
+        if verbose and ti % TURNS_PER_WINDOW == 0:
+            import torch
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            marks.append((agent.step_id, ev, time.perf_counter()))
         for k in range(ENV_STEPS_PER_TURN):
             s = agent.step_id
             i = s % len(frames_host)
@@ -201,6 +209,12 @@ def run_turns(agent, n_turns: int, frames_host, frames_dev, resident: bool, geom
                 if geom is not None and not resident:
                     h2d += geom["depth"][0].nbytes + 128
             agent.step_id += 1
+    if verbose and len(marks) > 1:
+        import torch
+        torch.cuda.synchronize()
+        print(("resident" if resident else "e2e") + " per-window ms (gpu/host): " +
+              " ".join(f"{sid}:{a.elapsed_time(b):.0f}/{1e3 * (tb - ta):.0f}" for (sid, a, ta), (_, b, tb) in zip(marks[:-1], marks[1:])),
+              file=sys.stderr, flush=True)
     return h2d, d2h
 
 

@@ -48,7 +48,9 @@ class StreamVLNConfig:
     max_depth: float = 10.0
     invalid_policy: int = INVALID_KEEP
     memory_cap: int = 1568                   # max memory tokens kept (oldest dropped first)
-    feat_cache_frames: int = 160             # per-stream LRU bound of the pooled-feature cache (1.4 MB per frame at 7B)
+    feat_cache_frames: Optional[int] = None  # per-stream LRU bound of the pooled-feature cache; None = from the byte budget
+    feat_cache_bytes: int = 8 << 30          # ... shared by all streams (1.4 MB per frame at 7B: 1 stream 1024 frames,
+                                             # 64 streams 89 frames each = 356 env steps; a miss only costs a re-encode)
 
     @staticmethod
     def tiny(vocab_size: int = 512, mode: str = "reference", layers: int = 2, max_pos: int = 4096) -> "StreamVLNConfig":
@@ -238,9 +240,16 @@ class StreamVLNForCausalLM:
             self.feat_episode[env_id] = episode_id
         return self.feat_cache[env_id]
 
+    def _cache_limit(self) -> int:
+        if self.config.feat_cache_frames is not None:
+            return self.config.feat_cache_frames
+        per_frame = self.tokens_per_frame * self.config.llm.hidden_size * 2
+        return max(16, min(1024, self.config.feat_cache_bytes // (per_frame * max(len(self.feat_cache), 1))))
+
     def _cache_put(self, cache, frame_id: int, feat: torch.Tensor) -> None:
         cache[frame_id] = feat
-        while len(cache) > self.config.feat_cache_frames:
+        limit = self._cache_limit()
+        while len(cache) > limit:
             cache.popitem(last=False)
 
     # ------------------------------------------------------------------ encode_rgbd
