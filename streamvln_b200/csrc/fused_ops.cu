@@ -74,32 +74,47 @@ rmsnorm_kernel(int4* __restrict__ x, const int4* __restrict__ r, const int4* __r
     }
 }
 
+// 4 independent (gate, up) chunk pairs per thread, every load issued before the first use: silu is a dependent chain of
+// ~30 instructions per element (precise expf and IEEE division, to round exactly like torch's bf16 silu), so with one
+// chunk per thread the kernel was latency/issue-bound at 4 TB/s (13.5 ms of a 64-stream packed turn, round 2 profile).
+constexpr int SW_UNROLL = 4;
 __global__ void __launch_bounds__(256)
 swiglu_kernel(const int4* __restrict__ gate_up, int64_t n_rows, int inter_i4, int4* __restrict__ out) {
-    const int64_t total = n_rows * inter_i4;
-    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
-         e += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t row = e / inter_i4;
-        const int c = (int)(e - row * inter_i4);
-        const int4 g = ld_stream(gate_up + row * 2 * inter_i4 + c);
-        const int4 u = ld_stream(gate_up + row * 2 * inter_i4 + inter_i4 + c);
-        const uint32_t* gu = reinterpret_cast<const uint32_t*>(&g);
-        const uint32_t* uu = reinterpret_cast<const uint32_t*>(&u);
-        int4 o;
-        uint32_t* ou = reinterpret_cast<uint32_t*>(&o);
+    const int64_t row = blockIdx.x;       // rows on x: a packed window-start prefill has > 65535 of them
+    const int4* grow = gate_up + row * 2 * inter_i4;
+    int4* orow = out + row * inter_i4;
+    const int c0 = (blockIdx.y * SW_UNROLL) * 256 + threadIdx.x;
+    int4 g[SW_UNROLL], u[SW_UNROLL];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            uint32_t res = 0;
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const float gv = bf16_bits_to_f32((gu[k] >> (16 * h)) & 0xFFFFu);
-                const float uv = bf16_bits_to_f32((uu[k] >> (16 * h)) & 0xFFFFu);
-                const float act = round_bf16(gv / (1.0f + expf(-gv)));  // silu in fp32, rounded like torch
-                res |= f32_to_bf16_bits(act * uv) << (16 * h);
-            }
-            ou[k] = res;
+    for (int i = 0; i < SW_UNROLL; ++i) {
+        const int c = c0 + i * 256;
+        if (c < inter_i4) {
+            g[i] = ld_stream(grow + c);
+            u[i] = ld_stream(grow + inter_i4 + c);
         }
-        st_stream(out + e, o);
+    }
+#pragma unroll
+    for (int i = 0; i < SW_UNROLL; ++i) {
+        const int c = c0 + i * 256;
+        if (c < inter_i4) {
+            const uint32_t* gu = reinterpret_cast<const uint32_t*>(&g[i]);
+            const uint32_t* uu = reinterpret_cast<const uint32_t*>(&u[i]);
+            int4 o;
+            uint32_t* ou = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                uint32_t res = 0;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const float gv = bf16_bits_to_f32((gu[k] >> (16 * h)) & 0xFFFFu);
+                    const float uv = bf16_bits_to_f32((uu[k] >> (16 * h)) & 0xFFFFu);
+                    const float act = round_bf16(gv / (1.0f + expf(-gv)));  // silu in fp32, rounded like torch
+                    res |= f32_to_bf16_bits(act * uv) << (16 * h);
+                }
+                ou[k] = res;
+            }
+            st_stream(orow + c, o);
+        }
     }
 }
 
@@ -177,12 +192,10 @@ int svln_swiglu(const void* gate_up, int64_t n_rows, int inter, void* out, svln_
     SVLN_REQUIRE(n_rows >= 0 && inter > 0 && inter % 8 == 0, SVLN_ERR_INVALID, "svln_swiglu: bad shape");
     if (n_rows == 0) return SVLN_OK;
     SVLN_REQUIRE(gate_up && out, SVLN_ERR_INVALID, "svln_swiglu: null pointer");
-    const int64_t total = n_rows * (inter / 8);
-    int64_t blocks = (total + 255) / 256;
-    const int64_t cap = (int64_t)sm_count() * 16;
-    if (blocks > cap) blocks = cap;
-    swiglu_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const int4*)gate_up, n_rows, inter / 8,
-                                                                       (int4*)out);
+    SVLN_REQUIRE(n_rows <= 0x7FFFFFFF, SVLN_ERR_RANGE, "svln_swiglu: %lld rows exceed the grid", (long long)n_rows);
+    const int inter_i4 = inter / 8;
+    dim3 grid((unsigned)n_rows, (unsigned)((inter_i4 + SW_UNROLL * 256 - 1) / (SW_UNROLL * 256)));
+    swiglu_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const int4*)gate_up, n_rows, inter_i4, (int4*)out);
     return check_launch("swiglu_kernel");
 }
 

@@ -187,3 +187,46 @@ def test_bench_window_alignment_and_peaks():
     pk = bench.peaks()
     assert pk["source"] in ("measured", "fallback") and pk["hbm_gbs"] > 1000 and pk["bf16_tflops"] >= pk["bf16_tflops_sustained"] > 100
     assert bench.ENV_STEPS_PER_TURN * bench.TURNS_PER_WINDOW == 32      # num_frames
+
+
+def test_run_episodes_refills_slots_and_keeps_the_cadence():
+    """scheduler.run_episodes (host logic, no GPU): E slots stream a longer list of episodes, a slot is refilled as soon
+    as its episode ends, the model runs on every 4th step of each episode, every episode gets exactly its own frames and
+    instruction, and results carry steps / turns / the action hash."""
+    from streamvln_b200.scheduler import hash_actions, run_episodes
+
+    class FakeEvaluator:
+        def __init__(self, n):
+            self.n, self.resets, self.model_steps, self.seen = n, [], [], {}
+
+        def reset_stream(self, i):
+            self.resets.append(i)
+
+        def step_all(self, live, frames, instructions, run_model, geom=None, preprocessed=None):
+            out = {}
+            for i in live:
+                ep = int(frames[i][0, 0, 0])                    # the frame source stamps the episode id
+                self.seen.setdefault(ep, []).append((int(frames[i][0, 0, 1]), run_model, instructions[i]))
+                if run_model:
+                    out[i] = [1 + (ep + len(self.seen[ep])) % 3]
+            if run_model:
+                self.model_steps.append(sorted(live))
+            return out
+
+    eps = [dict(id=i, length=L, instruction=f"go {i}") for i, L in enumerate((9, 4, 13, 5, 8))]
+    frame = lambda ep, step: np.full((2, 2, 3), 0, np.uint8) + np.array([ep, step, 0], np.uint8)
+    import numpy as np
+    ev = FakeEvaluator(2)
+    res = run_episodes(ev, eps, frame)
+    assert sorted(r.episode_id for r in res) == [0, 1, 2, 3, 4]
+    by = {r.episode_id: r for r in res}
+    for e in eps:
+        steps = ev.seen[e["id"]]
+        assert [s for s, _, _ in steps] == list(range(e["length"]))                     # its own frames, in order
+        assert [rm for _, rm, _ in steps] == [s % 4 == 0 for s in range(e["length"])]     # model on every 4th step
+        assert all(ins == e["instruction"] for _, _, ins in steps)
+        assert by[e["id"]].steps == e["length"] and by[e["id"]].turns == (e["length"] + 3) // 4
+    assert len(ev.resets) == 5 and ev.resets[:2] == [0, 1]                              # 2 initial fills + 3 refills
+    # the hash is a pure function of the action list
+    acts = [1 + (0 + k) % 3 for k in (1, 5, 9)]
+    assert by[0].action_hash == hash_actions(acts)
