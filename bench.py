@@ -54,6 +54,14 @@ STEP_DEF = ("1 bench step = 1 window of the stream = 8 model turns (1 window-sta
             "value counts env steps")
 
 
+def shared_config(mode: str, world: int):
+    """`config` of the JSON line - identical for `--impl ours` and `--impl reference` (the driver compares the two arms)."""
+    return {"workload": "configs[1]: StreamVLN LLaVA-Video-7B-Qwen2 single-episode streaming step per GPU, num_history=8, "
+                        "num_frames=32, num_future_steps=4, n_gen=5, bf16, random-init weights",
+            "mode": mode, "step_definition": STEP_DEF, "env_steps_per_step": ENV_STEPS_PER_STEP, "turns_per_step": TURNS_PER_WINDOW,
+            "episodes_per_gpu": 1, "parallelism": f"episode-sharded x{world}"}
+
+
 def peaks():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -522,12 +530,9 @@ def main_ours(a):
         "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": round(ms / K, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": "configs[1]: StreamVLN LLaVA-Video-7B-Qwen2 single-episode streaming step per GPU, num_history=8, "
-                               "num_frames=32, num_future_steps=4, n_gen=5, bf16, random-init weights",
-                   "mode": a.mode, "step_definition": STEP_DEF, "env_steps_per_step": ENV_STEPS_PER_STEP, "turns_per_step": TURNS_PER_WINDOW,
-                   "episodes_per_gpu": 1, "parallelism": f"episode-sharded x{world}",
-                   "l2": "working set (15 GB of weights per token) exceeds the 126 MB L2; no flush needed (microbench rows flush L2 per call)",
-                   "parity": "reference mode: pinned glue + HF-checked arithmetic (tests/); slowfast block: self-specified"},
+        "config": shared_config(a.mode, world),
+        "config_notes": {"l2": "working set (15 GB of weights per token) exceeds the 126 MB L2; no flush needed (microbench rows flush L2 per call)",
+                         "parity": "reference mode: pinned glue + HF-checked arithmetic (tests/); slowfast block: self-specified"},
         "e2e": {"value": round(e2e, 3), "unit": UNIT, "h2d_bytes_per_step": int(h2d / K) * world, "d2h_bytes_per_step": int(d2h / K) * world,
                 "ms_per_step": round(ms_e2e / K, 3)},
         "gpu_launches": int(launches),
@@ -626,10 +631,8 @@ def main_reference(a):
     out = {"impl": "reference", "metric": METRIC, "value": round(value, 4), "unit": UNIT, "n_gpus": int(os.environ.get("WORLD_SIZE", 1)),
            "steps": a.steps, "warmup": a.warmup, "ms_per_step": round(1e3 * total / a.steps, 2), "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-           "config": {"workload": "configs[1]: StreamVLN LLaVA-Video-7B-Qwen2 single-episode streaming step per GPU, num_history=8, "
-                                  "num_frames=32, num_future_steps=4, n_gen=5, bf16, random-init weights",
-                      "mode": "reference", "step_definition": STEP_DEF, "env_steps_per_step": ENV_STEPS_PER_STEP, "turns_per_step": TURNS_PER_WINDOW,
-                      "arm": "CPU path of the reference (oracle port) on the box's host cores"},
+           "config": shared_config("reference", int(os.environ.get("WORLD_SIZE", 1))),
+           "config_notes": {"arm": "CPU path of the reference (oracle port) on the box's host cores"},
            "cpu_baseline": {"value": round(value, 4), "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
            "e2e": {"value": round(value, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out), flush=True)
