@@ -7,7 +7,7 @@ everything between them is hand-written sm_100a CUDA behind the C-ABI: RMSNorm(+
 append, tcgen05 prefill attention, split-KV decode attention, SwiGLU, argmax.  Tokens of several streams (envs)
 are packed into one [n_tok, hidden] batch so every GEMM serves all concurrent episodes.  The single-stream decode -
 pure weight streaming - is ONE persistent kernel per generated token (`svln_decode_stack_step`, decode_stack.cu);
-2-4 streams use `svln_gemv` between the small kernels.
+`svln_gemv` serves the M = 1 (and the widest M = 2) linears of the launch-per-op path where it beats cuBLAS.
 """
 from __future__ import annotations
 
@@ -188,13 +188,20 @@ class Qwen2Engine:
         self.launches += 1
         return out
 
-    GEMV_MAX_M = 4
+    @staticmethod
+    def _gemv_wins(M: int, N: int, K: int) -> bool:
+        """Where svln_gemv beats cuBLAS on a B200 with a cold L2 (scripts/gemm_small_m.py, round 2; us, svln vs cuBLAS):
+        M = 1: qkv 16.7 / 28.9, gate_up 56.0 / 64.3, lm_head 172 / 194, o 15.3 / 15.2, down (K = 18944) 50.7 / 42.4;
+        M = 2: gate_up 61.4 / 64.0, lm_head 188 / 195, the rest lose; M >= 3: cuBLAS wins or ties everywhere (its
+        small-M kernels stream the weights just as well and handle the extra rows for free)."""
+        if K > 8192:
+            return False
+        return M == 1 or (M == 2 and N >= 32768)
 
     def _linear(self, x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, f32_out: bool = False) -> torch.Tensor:
-        """x [M,K] @ w[N,K]^T (+ bias).  M <= 4 (single-episode decode) streams the weights with svln_gemv; larger M are
-        GEMMs and go to cuBLAS."""
+        """x [M,K] @ w[N,K]^T (+ bias): svln_gemv where it is the faster weight stream (see _gemv_wins), else cuBLAS."""
         M = x.shape[0]
-        if M <= self.GEMV_MAX_M and self.use_gemv:
+        if self.use_gemv and M <= 4 and self._gemv_wins(M, w.shape[0], w.shape[1]):
             out = torch.empty(M, w.shape[0], dtype=torch.float32 if f32_out else torch.bfloat16, device=x.device)
             check(self.lib.svln_gemv(ptr(w), ptr(x), ptr(bias), ptr(out), M, w.shape[0], w.shape[1], 1 if f32_out else 0,
                                      cur_stream()))

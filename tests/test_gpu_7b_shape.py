@@ -177,7 +177,7 @@ def test_decode_stack_step_at_7b_dims(big, cuda, kv_len):
 def test_bf16_tie_goes_to_the_lowest_index_on_every_decode_path(big, cuda):
     """Two lm_head rows whose fp32 logits differ by far less than a bf16 ulp: HF (bf16 lm_head, .float(), argmax) sees
     a tie and takes the LOWER index although the higher row's unrounded sum is larger.  The fused stack (1 stream),
-    svln_gemv (2 streams) and cuBLAS (5 streams) must all agree."""
+    svln_gemv (the lm_head of 1 and 2 streams on the launch-per-op path) and cuBLAS (5 streams) must all agree."""
     from streamvln_b200.qwen2 import Chunk
 
     eng, lm32, lm16 = big
@@ -219,7 +219,7 @@ def test_bf16_tie_goes_to_the_lowest_index_on_every_decode_path(big, cuda):
         assert float(w2[hi]) > float(w2[lo]) and abs(float(w2[hi] - w2[lo])) < 2.0 ** -12 * abs(top), "nudge is not a near-tie"
         assert float(w2[hi].bfloat16()) == float(w2[lo].bfloat16()) == float(w2.bfloat16().max())
         picks = {}
-        for name, n, stack in (("stack", 1, True), ("gemv", 2, False), ("cublas", 5, False)):
+        for name, n, stack in (("stack", 1, True), ("gemv", 1, False), ("gemv2", 2, False), ("cublas", 5, False)):
             eng.use_stack = stack
             eng._graphs.clear()
             for env in range(n_env):
