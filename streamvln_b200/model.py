@@ -42,6 +42,9 @@ class StreamVLNConfig:
     eos_token_id: Optional[int] = None       # <|im_end|> with a real tokenizer; None = run to max_new_tokens
     tokenizer_model_max_length: Optional[int] = None
     mode: str = "reference"                  # "reference" | "slowfast"
+    memory: str = "sampled"                  # reference mode, what fills <memory> at a window start: "sampled" = the reference's
+                                             # num_history uniformly sampled frames; "voxel" = every past model-step frame,
+                                             # voxel-pruned (keep-latest-per-voxel, stable compaction, row gather: svln_voxel_prune)
     # slowfast only
     window_turns: int = 8                    # num_frames / num_future_steps
     voxel_size: float = 0.2
@@ -205,6 +208,10 @@ class StreamVLNForCausalLM:
         # per-frame pooled features of the CURRENT episode of each stream (an LRU; a miss only costs a re-encode)
         self.feat_cache: List["OrderedDict[int, torch.Tensor]"] = [OrderedDict() for _ in range(env_num)]
         self.feat_episode: List[Any] = [None] * env_num
+        # memory = "voxel": depth / pose / intrinsics of every model-step frame (device fp32), same keys as feat_cache
+        self.geom_cache: List[Dict[int, tuple]] = [dict() for _ in range(env_num)]
+        self.last_memory: List[Optional[torch.Tensor]] = [None] * env_num     # introspection (tests): rows spliced at <memory>
+        self._mem_pruner = None
         for e in range(env_num):
             self.engine.arena.reset_env(e)
         if self.config.mode == "slowfast":
@@ -228,6 +235,7 @@ class StreamVLNForCausalLM:
         """New episode on this stream: also drop the per-frame feature cache."""
         self.reset_for_env(env_idx)
         self.feat_cache[env_idx] = OrderedDict()
+        self.geom_cache[env_idx] = dict()
         self.feat_episode[env_idx] = None
         self.engine.arena.reset_env(env_idx)
 
@@ -237,6 +245,7 @@ class StreamVLNForCausalLM:
         to call reset_episode."""
         if self.feat_episode[env_id] != episode_id:
             self.feat_cache[env_id] = OrderedDict()
+            self.geom_cache[env_id] = dict()
             self.feat_episode[env_id] = episode_id
         return self.feat_cache[env_id]
 
@@ -250,7 +259,43 @@ class StreamVLNForCausalLM:
         cache[frame_id] = feat
         limit = self._cache_limit()
         while len(cache) > limit:
-            cache.popitem(last=False)
+            old, _ = cache.popitem(last=False)
+            for env, c in enumerate(self.feat_cache):
+                if c is cache:
+                    self.geom_cache[env].pop(old, None)
+
+    # ------------------------------------------------------------------ voxel-pruned slow memory (memory = "voxel")
+    def _remember_geometry(self, env_id: int, frame_ids, depths, poses, intrinsics) -> None:
+        g = self.geom_cache[env_id]
+        for i, f in enumerate(frame_ids):
+            if f not in g:
+                g[f] = (depths[0, i].to(self.device, torch.float32).contiguous(), poses[0, i].to(self.device, torch.float32).reshape(4, 4).contiguous(),
+                        intrinsics[0, i].to(self.device, torch.float32).reshape(4, 4).contiguous())
+
+    def _voxel_memory(self, env_id: int, before_frame: int) -> Optional[torch.Tensor]:
+        """north_star subsystem (1) as the reference's plumbing intended it (depths / poses / intrinsics reach encode_rgbd,
+        stream_video_vln.py:102, and are ignored): the <memory> block of a window start = the pooled tokens of EVERY past
+        model-step frame, back-projected to voxels, keep-latest-per-voxel, stably compacted and gathered by
+        svln_voxel_prune (one batched call), newest `memory_cap` survivors.  Returns [1, n, D] or None."""
+        cache, geom = self.feat_cache[env_id], self.geom_cache[env_id]
+        frames = sorted(f for f in cache if f in geom and f < before_frame)
+        if not frames:
+            return None
+        T = len(frames)
+        cfg = self.config
+        G = cfg.vision.pooled_per_side
+        if self._mem_pruner is None or self._mem_pruner.max_frames < T:
+            self._mem_pruner = VoxelPruner(VoxelPruneConfig(grid=G, dim=cfg.llm.hidden_size, voxel_size=cfg.voxel_size, max_depth=cfg.max_depth,
+                                                            invalid_policy=cfg.invalid_policy), 1, max(2 * T, 32), self.device)
+        depth = torch.stack([geom[f][0] for f in frames])[None]
+        pose = torch.stack([geom[f][1] for f in frames])[None]
+        intr = torch.stack([geom[f][2] for f in frames])[None]
+        feat = torch.stack([cache[f] for f in frames])[None].contiguous()
+        res = self._mem_pruner.prune(depth, pose, intr, feat)
+        self.engine.launches += 7
+        n = res.n_keep()                 # the one host read of a window start: the embed length depends on it
+        lo = max(0, n - cfg.memory_cap)
+        return res.feat[lo:n].clone()[None]
 
     # ------------------------------------------------------------------ encode_rgbd
     @torch.no_grad()
@@ -262,11 +307,20 @@ class StreamVLNForCausalLM:
         assert images.shape[0] == 1, "one stream per call (the reference call sites use batch size 1)"
         V = images.shape[1]
         feats = self._encode_views(images[0], env_id, frame_ids, episode_id)
+        voxel = self.config.memory == "voxel" and self.config.mode == "reference"
+        if voxel:
+            if frame_ids is None or depths is None or poses is None or intrinsics is None:
+                raise ValueError('memory="voxel" needs frame_ids and fp32 depths / poses / intrinsics with every request')
+            self._remember_geometry(env_id, frame_ids, depths, poses, intrinsics)
         start_idx = 0
         if time_ids is not None and time_ids[0] is not None and len(time_ids[0]):
             start_idx = time_ids[0][0]
         if V != 1 and start_idx != 0:
             nh = self.model.num_history
+            if voxel:
+                memory = self._voxel_memory(env_id, before_frame=frame_ids[-1])
+                self.last_memory[env_id] = memory
+                return feats[nh:], memory
             memory = feats[:nh].reshape(1, -1, feats.shape[-1])
             return feats[nh:], memory
         return feats, None

@@ -374,3 +374,70 @@ def test_from_pretrained_round_trip(tiny, cuda, tmp_path):
     r1 = m.generate(inputs=ids, images=frames, env_id=0, time_ids=[[0]], max_new_tokens=4, past_key_values=None)
     r2 = m2.generate(inputs=ids, images=frames, env_id=0, time_ids=[[0]], max_new_tokens=4, past_key_values=None)
     assert r1.sequences.tolist() == r2.sequences.tolist()
+
+
+def test_voxel_memory_window_start_matches_oracle(svln_lib, cuda):
+    """memory="voxel": at a window start the <memory> block is every past model-step frame's pooled tokens, pruned by
+    svln_voxel_prune (keys -> keep-latest -> compaction -> row gather).  72 env steps = two window starts (steps 32, 64)
+    over 8 and 16 past frames.  The spliced rows are BIT-EXACT against the C restatement on the same features and
+    geometry; the turn's ids are greedy under the oracle's logits with that block; ordinary turns are untouched."""
+    from streamvln_b200 import synth
+    from streamvln_b200.agent import VLNEvaluator
+    from streamvln_b200.model import StreamVLNConfig, StreamVLNForCausalLM
+    from streamvln_b200.tokenizer import StubQwenTokenizer
+
+    cfg = StreamVLNConfig.tiny(vocab_size=512, layers=3)
+    cfg.memory, cfg.memory_cap = "voxel", 1568
+    m = StreamVLNForCausalLM(cfg, n_env=1, device=cuda, seed=0, lm_head_std=0.3)
+    lm = _hf_from(m.weights)
+    m.reset(1)
+    n_steps = 72
+    st = synth.make_stream(n_steps, with_feat=False, seed=4)
+    args = SimpleNamespace(num_frames=32, num_future_steps=4, num_history=8, max_new_tokens=4)
+    ev = VLNEvaluator({"camera_intrinsic": synth.intrinsic_matrix()}, model=m, tokenizer=StubQwenTokenizer(512), args=args)
+    rng = np.random.default_rng(1)
+    frames = rng.integers(0, 255, size=(n_steps, 480, 640, 3), dtype=np.uint8)
+    got, ids, mems = [], [], {}
+    for s in range(n_steps):
+        a, _, _ = ev.step(0, frames[s], "leave the kitchen and wait by the stairs", run_model=(s % 4 == 0),
+                          depth=st["depth"][s], pose=st["pose"][s], intrinsic=st["intr"][s])
+        got.append(a)
+        if a is not None:
+            ids.append(ev.output_ids.cpu()[0].tolist())
+            if s in (32, 64):
+                mems[s] = m.last_memory[0].cpu()
+        ev.step_id += 1
+    G = cfg.vision.pooled_per_side
+
+    def memory_fn(before_frame):
+        past = [f for f in range(0, before_frame, 4)]
+        feats = torch.stack([m.feat_cache[0][f].cpu() for f in past])
+        return glue.voxel_memory(feats, st["depth"][past], st["pose"][past], st["intr"][past], G, cfg.voxel_size, cfg.max_depth,
+                                 cfg.invalid_policy, cfg.memory_cap)
+
+    for s in (32, 64):
+        want = memory_fn(s)
+        assert mems[s].shape == want.shape and torch.equal(mems[s].view(torch.int16), want.view(torch.int16)), s
+    n8, n16 = mems[32].shape[1], mems[64].shape[1]
+    assert 0 < n8 < min(8 * G * G, cfg.memory_cap) and n16 == cfg.memory_cap          # the second start hits the cap: the oldest survivors go
+    print(f"\n  voxel memory: {n8} of {8 * G * G} tokens kept at step 32, {n16} (the cap) of {16 * G * G} at step 64")
+    o = glue.ReferenceOracle(lm, num_history=8)
+    oa = glue.OracleAgent(o, StubQwenTokenizer(512), lambda i: m.feat_cache[0][i].float().cpu(), 32, 4, 8, 4)
+    oa.memory_fn = lambda f: memory_fn(f).float()
+    want, turn = [], 0
+    for s in range(n_steps):
+        run = s % 4 == 0
+        want.append(oa.step(0, "leave the kitchen and wait by the stairs", run_model=run, force_tokens=ids[turn] if run else None))
+        if run:
+            ok, _, gap = glue.greedy_consistent(oa.step_logits_log[-1], ids[turn])
+            assert ok, (turn, ids[turn], gap)
+            turn += 1
+        oa.step_id += 1
+    assert got == want
+    # the mode needs geometry with every request
+    m.reset(1)
+    ev2 = VLNEvaluator({"camera_intrinsic": synth.intrinsic_matrix()}, model=m, tokenizer=StubQwenTokenizer(512), args=args)
+    req = ev2.prepare(0, frames[0], "go", run_model=True)
+    req["depths"] = None
+    with pytest.raises(ValueError):
+        m.generate(**req)
