@@ -316,8 +316,18 @@ typedef struct svln_decode_stack {
     const int32_t* kv_len;       /* [n_stream] */
     void* workspace;             /* >= svln_decode_stack_workspace_bytes(), 256-byte aligned */
     size_t workspace_bytes;
+    const void* packed;          /* packed weight stream written by svln_decode_stack_pack, or NULL: the step then reads
+                                  * the row-major weights behind layer_ptrs / lm_head (slower; SVLN_STACK_FEED=0 forces it) */
+    size_t packed_bytes;
 } svln_decode_stack;
 size_t svln_decode_stack_workspace_bytes(const svln_decode_stack* desc);
+/* The decode step streams every weight byte exactly once per token.  svln_decode_stack_pack writes a second copy of the
+ * layer linears and lm_head (same bytes, `svln_decode_stack_packed_bytes` of them: 15.3 GB for Qwen2-7B) laid out as one
+ * contiguous stream per CTA in consumption order, which a single producer thread per SM feeds to shared memory with
+ * bulk copies (cp.async.bulk + mbarriers) across phase boundaries.  The layout depends on the SM count of the current
+ * device; pack on the device that runs the step.  `packed` 128-byte aligned.  Reads layer_ptrs (synchronises `stream`). */
+size_t svln_decode_stack_packed_bytes(const svln_decode_stack* desc);
+int svln_decode_stack_pack(const svln_decode_stack* desc, void* packed, size_t packed_bytes, svln_stream_t stream);
 /* SVLN_ERR_RANGE when n_stream > 1 (the caller falls back to the launch-per-op path; larger batches are GEMMs). */
 int svln_decode_stack_step(const svln_kv_arena* arena, const svln_decode_stack* desc, svln_stream_t stream);
 /* A grid barrier that times out (a bug, or a grid that could not be made co-resident) does not hang the GPU: the

@@ -52,6 +52,7 @@ class DecodeStackStruct(C.Structure):
         ("tok_in", C.c_void_p), ("tok_out", C.c_void_p), ("logits", C.c_void_p),
         ("seq_env", C.c_void_p), ("kv_len", C.c_void_p),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+        ("packed", C.c_void_p), ("packed_bytes", C.c_size_t),
     ]
 
 
@@ -97,6 +98,8 @@ PROTOTYPES = {
     "svln_argmax": (_i, [_vp, _i, _i64, _i64, _vp, _vp]),
     "svln_pool_bilinear": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
     "svln_decode_stack_workspace_bytes": (C.c_size_t, [C.POINTER(DecodeStackStruct)]),
+    "svln_decode_stack_packed_bytes": (C.c_size_t, [C.POINTER(DecodeStackStruct)]),
+    "svln_decode_stack_pack": (_i, [C.POINTER(DecodeStackStruct), _vp, _sz, _vp]),
     "svln_decode_stack_status": (_i, [C.POINTER(DecodeStackStruct), _vp, _vp]),
     "svln_decode_stack_trace": (_i, [_vp, _i]),
     "svln_decode_stack_step": (_i, [C.POINTER(KvArenaStruct), C.POINTER(DecodeStackStruct), _vp]),

@@ -94,7 +94,10 @@ __device__ __forceinline__ void group_sync() {
 // MODE 0: the whole item.  MODE 1: only issue the first DSTAGES - 1 K/V tiles (cp.async) and return - the fused
 // decode stack runs this BEFORE the grid barrier that publishes the step's new K/V row, to hide HBM and TLB latency.
 // MODE 2: the rest of the item after a MODE 1 call; the tile holding the newest key is loaded again first.
-template <int BAR_ID, int MODE = 0>
+// STAGES: depth of the K/V tile ring (a K and a V tile per stage).  FULL: the prologue requests STAGES tiles instead of
+// STAGES - 1 and a stage is refilled one iteration after it was consumed - the fused decode stack's packed-feed variant
+// runs the item with 2 stages (64 KB) and still has both tiles of its <= 128-key splits in flight before the barrier.
+template <int BAR_ID, int MODE = 0, int STAGES = DSTAGES, bool FULL = false>
 __device__ __forceinline__ void attn_decode_body(const DecodeParams& p, int split, int kvh, int z,
                                                  unsigned char* smem, int tid) {
     const int b = z / p.groups_per_seq, grp = z % p.groups_per_seq;
@@ -133,9 +136,10 @@ __device__ __forceinline__ void attn_decode_body(const DecodeParams& p, int spli
     const uint32_t smem_base = smem_u32(smem);
     const int n_tiles = (k_end - k_begin + DT - 1) / DT;
     // prologue
+    constexpr int PRO = FULL ? STAGES : STAGES - 1;   // tiles requested ahead of the first one consumed
     if (MODE != 2) {
 #pragma unroll
-        for (int s = 0; s < DSTAGES - 1; ++s) {
+        for (int s = 0; s < PRO; ++s) {
             if (s < n_tiles) {
                 load_tile_async(smem_base + s * 2 * TILE_BYTES, kplane, k_begin + s * DT, k_end, tid);
                 load_tile_async(smem_base + s * 2 * TILE_BYTES + TILE_BYTES, vplane, k_begin + s * DT, k_end, tid);
@@ -145,13 +149,13 @@ __device__ __forceinline__ void attn_decode_body(const DecodeParams& p, int spli
         if (MODE == 1) return;
     } else {
         // the prologue tiles were requested before the newest key (kv_hi - 1) was published: fetch its tile again
+        // (waited for below, after the Q loads have been issued: one L2 round trip instead of two)
         const int t_new = (kv_hi - 1 - k_begin) / DT;
-        if (k_end == kv_hi && t_new < DSTAGES - 1) {
+        if (k_end == kv_hi && t_new < PRO) {
             load_tile_async(smem_base + t_new * 2 * TILE_BYTES, kplane, k_begin + t_new * DT, k_end, tid);
             load_tile_async(smem_base + t_new * 2 * TILE_BYTES + TILE_BYTES, vplane, k_begin + t_new * DT, k_end, tid);
         }
         cp_async_commit();
-        cp_async_wait<0>();
     }
 
     // Q fragments: rows gid and gid+8; row r -> token tok0 + r / g, head kvh*g + r % g
@@ -172,6 +176,7 @@ __device__ __forceinline__ void attn_decode_body(const DecodeParams& p, int spli
         }
     }
 
+    if (MODE == 2) cp_async_wait<0>();
     AD_TRACE(1);
     float o[16][4];
 #pragma unroll
@@ -180,19 +185,19 @@ __device__ __forceinline__ void attn_decode_body(const DecodeParams& p, int spli
     float l_run[2] = {0.f, 0.f};
 
     for (int it = 0; it < n_tiles; ++it) {
-        cp_async_wait<DSTAGES - 2>();
+        cp_async_wait<PRO - 1>();
         group_sync<BAR_ID>();
         if (it == 0) AD_TRACE(2);
         {   // refill the stage consumed in the previous iteration
-            const int nt = it + DSTAGES - 1;
-            if (nt < n_tiles) {
-                const int s = nt % DSTAGES;
+            const int nt = it + STAGES - 1;
+            if (nt < n_tiles && (!FULL || it >= 1)) {
+                const int s = nt % STAGES;
                 load_tile_async(smem_base + s * 2 * TILE_BYTES, kplane, k_begin + nt * DT, k_end, tid);
                 load_tile_async(smem_base + s * 2 * TILE_BYTES + TILE_BYTES, vplane, k_begin + nt * DT, k_end, tid);
             }
             cp_async_commit();
         }
-        const uint32_t ktile = smem_base + (it % DSTAGES) * 2 * TILE_BYTES;
+        const uint32_t ktile = smem_base + (it % STAGES) * 2 * TILE_BYTES;
         const uint32_t vtile = ktile + TILE_BYTES;
         const int key_base = k_begin + it * DT + warp * 16;
         if (key_base >= k_end) continue;  // warp-uniform: this warp's 16 keys are all out of range

@@ -42,6 +42,8 @@
 // modules; accumulation order differs from cuBLAS, which the parity tolerance (1e-2 on logits) covers.
 #include <stdlib.h>
 
+#include <vector>
+
 #include "attn_decode_body.cuh"
 
 namespace svln {
@@ -58,6 +60,9 @@ constexpr int MK_MAX_SPLITS = 32;
 constexpr int MK_XPAD = 32;          // elements between the x rows of two streams: 64 B, spreads the banks
 constexpr int MK_MISC = 4096;        // bytes of misc shared memory (reductions, flags, combine weights)
 constexpr unsigned MK_SPIN_LIMIT = 1u << 22;
+// CTA-wide barrier of the MK_THREADS compute threads: a named barrier, so that the packed-stream variant can run a
+// ninth (producer) warp that never joins it.  With exactly MK_THREADS threads in the CTA it is __syncthreads().
+#define MK_SYNC() asm volatile("bar.sync 2, %0;" ::"n"(MK_THREADS) : "memory")
 
 struct StackParams {
     svln_kv_arena arena;
@@ -79,6 +84,7 @@ struct StackParams {
     int dbg;                      // SVLN_STACK_DBG (debug) bit 0: skip preambles, 1: skip GEMV main loop, 2: skip epilogues
     int stop_after;               // SVLN_STACK_STOP (debug): return after this many phases, 0 = run everything
     long long* trace;             // SVLN_STACK_TRACE: clock64 stamps of CTA 0 [layer][phase 0..5][point 0..7], else nullptr
+    const unsigned char* packed;  // packed weight stream (svln_decode_stack_pack) or nullptr
 };
 
 __device__ __forceinline__ unsigned long long mk_globaltimer() {
@@ -138,7 +144,7 @@ __device__ __forceinline__ float ld_cg_f32(const float* p) {
 // index instead of hanging the GPU: every later wait falls through, the kernel ends with garbage, and CTA 0 reports
 // token -1 so the caller fails loudly (sync[2], sync[3] = CTA, count seen).
 __device__ __forceinline__ void grid_arrive(unsigned* sync, unsigned& epoch, int G) {
-    __syncthreads();
+    MK_SYNC();
     epoch += (unsigned)G;
     if (threadIdx.x == 0) {
         __threadfence();
@@ -163,7 +169,7 @@ __device__ __forceinline__ void grid_wait(unsigned* sync, unsigned epoch, int G)
             }
         }
     }
-    __syncthreads();
+    MK_SYNC();
 }
 
 // ---- weight-streaming GEMV core -------------------------------------------------------------------------------
@@ -355,7 +361,7 @@ __device__ __forceinline__ void gemv_phase(const StackParams& p, unsigned char* 
             const int nr = nu * RPU, nb = (nr + 15) >> 4;
             if (tid <= nb) rowmap[MK_CAP + tid] = (tid * nr) / nb;   // balanced blocks of <= 16 rows
         }
-        __syncthreads();
+        MK_SYNC();
         const int nrows = nu * RPU, nblk = (nrows + 15) >> 4;
         const int sb = nblk >= 4 ? 4 : (nblk >= 2 ? 2 : 1);     // blocks advancing together (ILP) vs ring depth
         GemvCursor cur;
@@ -371,7 +377,7 @@ __device__ __forceinline__ void gemv_phase(const StackParams& p, unsigned char* 
         else if (sb == 4) gemv_finish<NB, 4>(cur, W, K, rowmap, nrows, xs, p.xs_stride, part, ring, pol);
         else if (sb == 2) gemv_finish<NB, 2>(cur, W, K, rowmap, nrows, xs, p.xs_stride, part, ring, pol);
         else gemv_finish<NB, 1>(cur, W, K, rowmap, nrows, xs, p.xs_stride, part, ring, pol);
-        __syncthreads();
+        MK_SYNC();
         MK_TRACE(tr_li, tr_ph, 4);
         MK_GT(tr_li, tr_ph * 3 + 1);
         for (int i = tid; i < nu * NB && !(p.dbg & 4); i += MK_THREADS) {
@@ -385,7 +391,7 @@ __device__ __forceinline__ void gemv_phase(const StackParams& p, unsigned char* 
             }
             epi(u0 + j, n, s);
         }
-        __syncthreads();
+        MK_SYNC();
     }
     MK_TRACE(tr_li, tr_ph, 5);
     MK_GT(tr_li, tr_ph * 3 + 2);
@@ -456,7 +462,7 @@ __device__ __forceinline__ void preamble_norm(const StackParams& p, unsigned cha
         ss = warp_sum(ss);
         if (lane == 0) red[n * MK_WARPS + warp] = ss;
     }
-    __syncthreads();
+    MK_SYNC();
 #pragma unroll
     for (int n = 0; n < NB; ++n) {
         float tot = 0.f;
@@ -483,7 +489,7 @@ __device__ __forceinline__ void preamble_norm(const StackParams& p, unsigned cha
             }
         }
     }
-    __syncthreads();
+    MK_SYNC();
 }
 
 // x = src[NB][K] (written earlier in this launch by other CTAs) into shared memory, 8 loads in flight per thread
@@ -508,7 +514,7 @@ __device__ __forceinline__ void preamble_copy(const StackParams& p, unsigned cha
             }
         }
     }
-    __syncthreads();
+    MK_SYNC();
 }
 
 // merge the split partials of (stream b, kv head kvh): warp <-> query row, lane <-> 4 dims; same arithmetic and
@@ -548,13 +554,282 @@ __device__ __noinline__ void combine_splits(const StackParams& p, int b, int kvh
     }
 }
 
-template <int MODE>
+template <int MODE, int STAGES = DSTAGES>
 __device__ __noinline__ void attn_item(const DecodeParams& dp, int split, int kvh, int b, unsigned char* smem, int tid) {
-    attn_decode_body<1, MODE>(dp, split, kvh, b, smem, tid);
+    attn_decode_body<1, MODE, STAGES, STAGES != DSTAGES>(dp, split, kvh, b, smem, tid);
 }
 
-template <int NB>
-__global__ void __launch_bounds__(MK_THREADS, 1)
+
+// ---- packed weight stream (FEED = 1) ------------------------------------------------------------------------------
+// svln_decode_stack_pack re-lays the weights of the step once: every CTA's share of every linear, in the order the CTA
+// consumes it, as ONE contiguous byte stream per CTA (layer by layer: QKV, O, gate/up, down; then lm_head).  A ninth
+// warp (one thread) walks that stream with 1-D bulk copies (cp.async.bulk, L2 evict-first) into a ring of TK_SLOTS x
+// 16 KB stages guarded by full/empty mbarriers.  It knows nothing of phases or grid barriers, so it keeps streaming
+// while the compute warps sit in an epilogue, a grid barrier, a preamble or the attention phase: every phase starts
+// on a full ring (112 KB per SM, 16.6 MB chip-wide; all of a CTA's O slice is resident before the attention phase
+// ends), and the 3-6 k cycles of LDGSTS issue per phase (profiles/r2_decode_stack_experiments.md) are gone.  Measured
+// first with scripts/tma_stream_probe.cu: one thread per SM sustains 6.1-6.3 TB/s with 16-32 KB copies (2-D tensor
+// boxes of fewer than ~128 rows do not: 100-200 ns per box).
+// Layout of one stage: [k32-step][row of the group][64 B]: lane (g, t) of the warp that owns a k32-step reads the
+// 16 bytes t of rows 16 b + g and 16 b + g + 8 - 512 contiguous bytes per warp load, conflict-free without a swizzle.
+// Rows of a CTA are taken in balanced groups of <= 32 rows (QKV, O, down: the 8 warps interleave over the k32-steps
+// of a stage, as in the LDGSTS variant) or <= 256 rows (gate/up, lm_head: one k32-step fills a stage, warp w owns row
+// blocks w and w + 8 and sweeps every k-step itself: no cross-warp sum).
+constexpr int TK_SLOT_BYTES = 32768;
+constexpr int TK_SLOTS = 3;
+constexpr int TK_ATTN_STAGES = 2;                  // K/V tile stages of the in-kernel attention item: 64 KB
+constexpr int TK_ATTN_SMEM = TK_ATTN_STAGES * 2 * TILE_BYTES;
+constexpr int TK_WIDE_ROWS = 256;
+constexpr int TK_NARROW_ROWS = 32;
+constexpr int TK_BAR_OFF = 256;                    // full[TK_SLOTS], empty[TK_SLOTS] inside the misc block
+constexpr int TK_MISC = 512;                       // the misc block of the packed-feed variant (MK_MISC otherwise); the final
+                                                   // argmax reduction borrows the partial-sum buffer instead
+
+struct TkDims { int n_layer, D, I, Hq, Hkv, V, G; };
+struct TkPhase { int n_total, rpu, K, wide; };
+// balanced contiguous ranges; 32-bit arithmetic (n * G < 2^31 is checked on the host: 64-bit divisions are subroutine
+// calls on the GPU and these sit between a grid barrier and the first weight byte)
+__host__ __device__ inline int tk_lo(int n, int c, int G) { return (int)((unsigned)n * (unsigned)c / (unsigned)G); }
+// the c with tk_lo(n, c, G) <= u < tk_lo(n, c + 1, G)
+__host__ __device__ inline int tk_owner(int u, int n, int G) {
+    return (int)((((unsigned)u + 1u) * (unsigned)G + (unsigned)n - 1u) / (unsigned)n) - 1;
+}
+__host__ __device__ inline int tk_groups(int n_units, int rpu, int wide) {
+    const int cap = (wide ? TK_WIDE_ROWS : TK_NARROW_ROWS) / rpu;
+    return (n_units + cap - 1) / cap;
+}
+__host__ __device__ inline int tk_ks(int rows, int wide) {     // k32-steps per stage
+    const int fit = TK_SLOT_BYTES / (rows * 64);
+    (void)wide;
+    return fit < 1 ? 1 : fit;
+}
+// phases: 0 QKV (units = RoPE pairs), 1 O, 2 gate/up (units = gate/up pairs), 3 down, 4 lm_head
+__host__ __device__ inline TkPhase tk_phase(const TkDims& d, int ph) {
+    switch (ph) {
+        case 0: return {(d.Hq + 2 * d.Hkv) * 64, 2, d.D, 0};
+        case 1: return {d.D, 1, d.Hq * 128, 0};
+        case 2: return {d.I, 2, d.D, 1};
+        case 3: return {d.D, 1, d.I, 0};
+        default: return {d.V, 1, d.D, 1};
+    }
+}
+// bytes of one layer that belong to CTAs 0..c-1
+__host__ __device__ inline long long tk_layer_before(const TkDims& d, int c) {
+    long long b = 0;
+    for (int ph = 0; ph < 4; ++ph) {
+        const TkPhase P = tk_phase(d, ph);
+        b += (long long)tk_lo(P.n_total, c, d.G) * P.rpu * P.K * 2;
+    }
+    return b;
+}
+__host__ __device__ inline long long tk_cta_base(const TkDims& d, int c) {
+    return (long long)d.n_layer * tk_layer_before(d, c) + (long long)tk_lo(d.V, c, d.G) * d.D * 2;
+}
+
+struct TkFeed { uint32_t ring, full, empty; unsigned slot, par; unsigned* sync; const int* gate; };
+
+__device__ __forceinline__ void tk_mbar_init(uint32_t bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void tk_mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tk_mbar_expect(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool tk_mbar_try(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+// a wait that cannot hang the GPU: after ~2^20 polls (seconds) it raises the abort flag of the grid barrier.
+// SLEEP_NS > 0 (the producer thread): back off between polls - a thread that spins on try_wait competes with the
+// compute warps for the SM's MIO queue (the attention item got 45 % slower with a spinning producer).
+template <int SLEEP_NS = 0>
+__device__ __forceinline__ void tk_mbar_wait(uint32_t bar, uint32_t parity, unsigned* sync) {
+    unsigned polls = 0;
+    while (!tk_mbar_try(bar, parity)) {
+        if (SLEEP_NS > 0) __nanosleep(SLEEP_NS);
+        if ((++polls & 4095u) == 0) {
+            unsigned ab;
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(ab) : "l"(sync + 1) : "memory");
+            if (ab != 0) return;
+            if (polls > (1u << 20)) { atomicCAS(sync + 1, 0u, 0x7FFFu); return; }
+        }
+    }
+}
+
+// the producer thread: walks the CTA's packed stream stage by stage, in the order gemv_phase_tk consumes it
+__device__ __noinline__ void tk_producer(const StackParams& p, TkFeed f, uint64_t pol) {
+    const TkDims d = {p.n_layer, p.D, p.I, p.Hq, p.Hkv, p.V, p.G};
+    const int c = blockIdx.x;
+    const unsigned char* src = p.packed + tk_cta_base(d, c);
+    unsigned slot = 0, par = 1, filled = 0;      // par: parity of the empty barrier's phase to wait for (first lap: none)
+    int phases_left = p.stop_after > 0 ? p.stop_after : 0x7FFFFFFF;
+    int cur_li = 0;
+    auto run = [&](int ph) {
+        const TkPhase P = tk_phase(d, ph);
+        const int u0 = tk_lo(P.n_total, c, d.G), nu = tk_lo(P.n_total, c + 1, d.G) - u0;
+        if (nu <= 0) return;
+        const int ng = tk_groups(nu, P.rpu, P.wide), KT = P.K >> 5;
+        for (int gi = 0; gi < ng; ++gi) {
+            const int rows = (tk_lo(nu, gi + 1, ng) - tk_lo(nu, gi, ng)) * P.rpu;
+            const int KS = tk_ks(rows, P.wide);
+            for (int s0 = 0; s0 < KT; s0 += KS) {
+                const uint32_t bytes = (uint32_t)(min(KS, KT - s0) * rows * 64);
+                long long* tkt = nullptr;
+                if (p.trace && c == 0 && cur_li == p.n_layer / 2 && ph < 4 && gi == 0 && s0 / KS < 100)
+                    tkt = p.trace + (int64_t)(p.n_layer + 1) * 6 * 8 + 8 + 160 * 16 + 2048 + (ph * 100 + s0 / KS) * 2;
+                if (tkt) tkt[0] = clock64();
+                if (filled >= TK_SLOTS) tk_mbar_wait<0>(f.empty + slot * 8, par, f.sync);
+                else ++filled;
+                if (tkt) tkt[1] = clock64();
+                tk_mbar_expect(f.full + slot * 8, bytes);
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                             ::"r"(f.ring + slot * TK_SLOT_BYTES), "l"(src), "r"(bytes), "r"(f.full + slot * 8), "l"(pol) : "memory");
+                src += bytes;
+                if (++slot == TK_SLOTS) { slot = 0; par ^= 1u; }
+            }
+        }
+    };
+    for (int li = 0; li < p.n_layer; ++li) {
+        cur_li = li;
+        run(0); if (--phases_left == 0) return;
+        if (--phases_left == 0) return;                    // attention: no weights
+        if (p.dbg & 8) {                                   // experiment: hold the O slice back until this CTA's attention work is done
+            const volatile int* gate = reinterpret_cast<const volatile int*>(f.gate);
+            unsigned polls = 0;
+            while (*gate < li + 1 && ++polls < (1u << 22)) __nanosleep(64);
+        }
+        run(1); if (--phases_left == 0) return;
+        run(2); if (--phases_left == 0) return;
+        run(3); if (--phases_left == 0) return;
+    }
+    run(4);
+}
+
+// One GEMV phase of this CTA fed from the packed stream; same contract as gemv_phase (mid: wait for the previous phase
+// and build x; epi(unit, n, sums[RPU])).
+template <int NB, int RPU, bool WIDE, class MidFn, class EpiFn>
+__device__ __forceinline__ void gemv_phase_tk(const StackParams& p, unsigned char* smem, TkFeed& f, int K, int n_units,
+                                              MidFn mid, EpiFn epi, int tr_li, int tr_ph) {
+    const __nv_bfloat16* xs = reinterpret_cast<const __nv_bfloat16*>(smem);
+    float* part = reinterpret_cast<float*>(smem + p.off_part);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    constexpr int KW = WIDE ? 1 : MK_WARPS;               // warps that share a row
+    // geometry of the first group before the grid barrier is waited for (integer divisions off the critical path)
+    const int ng = n_units > 0 ? tk_groups(n_units, RPU, WIDE) : 0, KT = K >> 5;
+    const int blk0 = WIDE ? warp : 0, blk1 = WIDE ? warp + MK_WARPS : 1;      // this warp's two row blocks
+    int gu0 = 0, nu = ng > 0 ? tk_lo(n_units, 1, ng) : 0;
+    int rows = nu * RPU, KS = rows > 0 ? tk_ks(rows, WIDE) : 1;
+    const uint32_t xv = smem_u32(xs + (g < NB ? g : 0) * p.xs_stride) + t * 16;
+    MK_TRACE(tr_li, tr_ph, 0);
+    MK_TRACE(tr_li, tr_ph, 2);
+    mid();
+    MK_TRACE(tr_li, tr_ph, 3);
+    for (int gi = 0; gi < ng; ++gi) {
+        // rows past the group's end re-read its last row (their sums are never used)
+        const uint32_t r00 = (uint32_t)min(blk0 * 16 + g, rows - 1) * 64, r01 = (uint32_t)min(blk0 * 16 + g + 8, rows - 1) * 64;
+        const uint32_t r10 = (uint32_t)min(blk1 * 16 + g, rows - 1) * 64, r11 = (uint32_t)min(blk1 * 16 + g + 8, rows - 1) * 64;
+        const bool has0 = blk0 * 16 < rows, has1 = blk1 * 16 < rows;
+        const uint32_t step_bytes = (uint32_t)rows * 64;
+        float acc[2][2][4];
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[j][0][e] = acc[j][1][e] = 0.f;
+        for (int s0 = 0; s0 < KT; s0 += KS) {
+            const int ksn = min(KS, KT - s0);
+            long long* tkt = nullptr;
+            if (p.trace && blockIdx.x == 0 && tid == 0 && tr_li == p.n_layer / 2 && gi == 0 && s0 / KS < 100)
+                tkt = p.trace + (int64_t)(p.n_layer + 1) * 6 * 8 + 8 + 160 * 16 + (tr_ph * 100 + s0 / KS) * 4;
+            if (tkt) tkt[0] = clock64();
+            tk_mbar_wait(f.full + f.slot * 8, f.par, f.sync);
+            if (tkt) tkt[1] = clock64();
+            const uint32_t base = f.ring + f.slot * TK_SLOT_BYTES + t * 16;
+            if (!(p.dbg & 2) && has0) {
+                // narrow: warp w owns the k32-steps whose index in the whole sweep is w mod 8 (fixed summation order)
+#pragma unroll 2
+                for (int s = WIDE ? 0 : ((warp - s0) & (MK_WARPS - 1)); s < ksn; s += KW) {
+                    const int4 x = lds128u(xv + (s0 + s) * 64);
+                    const uint32_t sb = base + (uint32_t)s * step_bytes;
+                    {
+                        const int4 w0 = lds128u(sb + r00), w1 = lds128u(sb + r01);
+                        const uint32_t a0[4] = {(uint32_t)w0.x, (uint32_t)w1.x, (uint32_t)w0.y, (uint32_t)w1.y};
+                        const uint32_t a1[4] = {(uint32_t)w0.z, (uint32_t)w1.z, (uint32_t)w0.w, (uint32_t)w1.w};
+                        mma_bf16(acc[0][0], a0, (uint32_t)x.x, (uint32_t)x.y);
+                        mma_bf16(acc[0][1], a1, (uint32_t)x.z, (uint32_t)x.w);
+                    }
+                    if (has1) {
+                        const int4 w0 = lds128u(sb + r10), w1 = lds128u(sb + r11);
+                        const uint32_t a0[4] = {(uint32_t)w0.x, (uint32_t)w1.x, (uint32_t)w0.y, (uint32_t)w1.y};
+                        const uint32_t a1[4] = {(uint32_t)w0.z, (uint32_t)w1.z, (uint32_t)w0.w, (uint32_t)w1.w};
+                        mma_bf16(acc[1][0], a0, (uint32_t)x.x, (uint32_t)x.y);
+                        mma_bf16(acc[1][1], a1, (uint32_t)x.z, (uint32_t)x.w);
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) tk_mbar_arrive(f.empty + f.slot * 8);
+            if (tkt) tkt[2] = clock64();
+            if (++f.slot == TK_SLOTS) { f.slot = 0; f.par ^= 1u; }
+        }
+        // partial sums: part[(kw * TK_WIDE_ROWS + row) * NB + n], kw = warp (narrow) or 0 (wide)
+        {
+            float* pw = part + (int64_t)(WIDE ? 0 : warp) * TK_WIDE_ROWS * NB;
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int r0 = (j == 0 ? blk0 : blk1) * 16 + g;
+                if (WIDE && !(j == 0 ? has0 : has1)) continue;
+                if (r0 < rows) {
+                    if (2 * t < NB) pw[r0 * NB + 2 * t] = acc[j][0][0] + acc[j][1][0];
+                    if (2 * t + 1 < NB) pw[r0 * NB + 2 * t + 1] = acc[j][0][1] + acc[j][1][1];
+                }
+                if (r0 + 8 < rows) {
+                    if (2 * t < NB) pw[(r0 + 8) * NB + 2 * t] = acc[j][0][2] + acc[j][1][2];
+                    if (2 * t + 1 < NB) pw[(r0 + 8) * NB + 2 * t + 1] = acc[j][0][3] + acc[j][1][3];
+                }
+            }
+        }
+        MK_SYNC();
+        MK_TRACE(tr_li, tr_ph, 4);
+        MK_GT(tr_li, tr_ph * 3 + 1);
+        for (int i = tid; i < nu * NB && !(p.dbg & 4); i += MK_THREADS) {
+            const int j = i / NB, n = i % NB;
+            float s[RPU];
+#pragma unroll
+            for (int q = 0; q < RPU; ++q) {
+                float a = 0.f;
+#pragma unroll
+                for (int w = 0; w < KW; ++w) a += part[((int64_t)w * TK_WIDE_ROWS + j * RPU + q) * NB + n];
+                s[q] = a;
+            }
+            epi(gu0 + j, n, s);
+        }
+        MK_SYNC();
+        if (gi + 1 < ng) {                                 // next group's geometry
+            gu0 = tk_lo(n_units, gi + 1, ng);
+            nu = tk_lo(n_units, gi + 2, ng) - gu0;
+            rows = nu * RPU;
+            KS = tk_ks(rows, WIDE);
+        }
+    }
+    MK_TRACE(tr_li, tr_ph, 5);
+    MK_GT(tr_li, tr_ph * 3 + 2);
+}
+
+template <int NB, int RPU, bool WIDE, int FEED, class RowFn, class MidFn, class EpiFn>
+__device__ __forceinline__ void run_gemv(const StackParams& p, unsigned char* smem, TkFeed& feed, const __nv_bfloat16* W,
+                                         int K, int n_units, RowFn rowfn, MidFn mid, EpiFn epi, uint64_t pol, int tr_li,
+                                         int tr_ph) {
+    if constexpr (FEED == 1) gemv_phase_tk<NB, RPU, WIDE>(p, smem, feed, K, n_units, mid, epi, tr_li, tr_ph);
+    else gemv_phase<NB, RPU>(p, smem, W, K, n_units, rowfn, mid, epi, pol, tr_li, tr_ph);
+}
+
+template <int NB, int FEED>
+__global__ void __launch_bounds__(MK_THREADS + FEED * 32, 1)
 decode_stack_kernel(const __grid_constant__ StackParams p) {
     extern __shared__ __align__(1024) unsigned char smem[];
     const int tid = threadIdx.x, warp = tid >> 5;
@@ -569,6 +844,22 @@ decode_stack_kernel(const __grid_constant__ StackParams p) {
     int* s_qstart = s_misc_i + 36;  // [NB]
     int* s_nq = s_misc_i + 40;      // [NB]
     if (tid < NB) { s_qstart[tid] = tid; s_nq[tid] = 1; }
+    if (tid == 0) s_misc_i[44] = 0;
+    TkFeed feed = {0, 0, 0, 0, 0, p.sync, s_misc_i + 44};
+    if constexpr (FEED == 1) {
+        feed.ring = smem_u32(smem + p.off_ring);
+        feed.full = smem_u32(smem + p.off_misc + TK_BAR_OFF);
+        feed.empty = feed.full + TK_SLOTS * 8;
+        if (tid == 0) {
+            for (int s = 0; s < TK_SLOTS; ++s) { tk_mbar_init(feed.full + s * 8, 1); tk_mbar_init(feed.empty + s * 8, MK_WARPS); }
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();                                 // all nine warps, once
+        if (warp == MK_WARPS) {
+            if ((tid & 31) == 0) tk_producer(p, feed, pol);
+            return;
+        }
+    }
 
     // this CTA's share of each phase (balanced contiguous ranges)
     const int n_pairs_all = (Hq + 2 * Hkv) * 64;
@@ -625,8 +916,22 @@ decode_stack_kernel(const __grid_constant__ StackParams p) {
         const __nv_bfloat16* ln2 = reinterpret_cast<const __nv_bfloat16*>(__ldg(L + 6));
 
         // ---- QKV: hn = h (+ pending MLP output); x = RMSNorm(hn); q,k,v = x W^T + b; RoPE; append
-        gemv_phase<NB, 2>(p, smem, wqkv, D, qkv_p1 - qkv_p0, qkv_row,
+        // bias and RoPE factors of this thread's epilogue unit are fetched before the barrier is waited for (they do not
+        // depend on this step): the epilogue then needs no load at all
+        const bool q_pre = NB == 1 && qkv_p1 - qkv_p0 <= 16;
+        float q_b0 = 0.f, q_b1 = 0.f, q_c0 = 0.f, q_s0 = 0.f, q_c1 = 0.f, q_s1 = 0.f;
+        run_gemv<NB, 2, false, FEED>(p, smem, feed, wqkv, D, qkv_p1 - qkv_p0, qkv_row,
             [&] {
+                if (q_pre && tid < qkv_p1 - qkv_p0) {
+                    const int pr = qkv_p0 + tid, h = pr >> 6, d = pr & 63, row = h * 128 + d;
+                    if (bqkv) { q_b0 = __bfloat162float(bqkv[row]); q_b1 = __bfloat162float(bqkv[row + 64]); }
+                    if (h < Hq + Hkv) {
+                        const __nv_bfloat16* cr = p.cos_t + (int64_t)pos[0] * HD;
+                        const __nv_bfloat16* sr = p.sin_t + (int64_t)pos[0] * HD;
+                        q_c0 = __bfloat162float(cr[d]); q_s0 = __bfloat162float(sr[d]);
+                        q_c1 = __bfloat162float(cr[d + 64]); q_s1 = __bfloat162float(sr[d + 64]);
+                    }
+                }
                 if (li > 0) grid_wait(p.sync, epoch, G);     // previous layer's down projection
                 MK_TRACE(li, 0, 1);
                 MK_GT(li, 0);
@@ -635,16 +940,16 @@ decode_stack_kernel(const __grid_constant__ StackParams p) {
             [&](int u, int n, const float (&s)[2]) {
                 const int pr = qkv_p0 + u, h = pr >> 6, d = pr & 63;
                 const int row = h * 128 + d;
-                const float xl = round_bf16(s[0] + (bqkv ? __bfloat162float(bqkv[row]) : 0.f));
-                const float xh = round_bf16(s[1] + (bqkv ? __bfloat162float(bqkv[row + 64]) : 0.f));
+                const float xl = round_bf16(s[0] + (q_pre ? q_b0 : (bqkv ? __bfloat162float(bqkv[row]) : 0.f)));
+                const float xh = round_bf16(s[1] + (q_pre ? q_b1 : (bqkv ? __bfloat162float(bqkv[row + 64]) : 0.f)));
                 __nv_bfloat16 lo, hi;
                 if (h < Hq + Hkv) {
                     const __nv_bfloat16* cr = p.cos_t + (int64_t)pos[n] * HD;
                     const __nv_bfloat16* sr = p.sin_t + (int64_t)pos[n] * HD;
-                    const float a = round_bf16(__fmul_rn(xl, __bfloat162float(cr[d])));
-                    const float b = round_bf16(__fmul_rn(-xh, __bfloat162float(sr[d])));
-                    const float cc = round_bf16(__fmul_rn(xh, __bfloat162float(cr[d + 64])));
-                    const float dd = round_bf16(__fmul_rn(xl, __bfloat162float(sr[d + 64])));
+                    const float a = round_bf16(__fmul_rn(xl, q_pre ? q_c0 : __bfloat162float(cr[d])));
+                    const float b = round_bf16(__fmul_rn(-xh, q_pre ? q_s0 : __bfloat162float(sr[d])));
+                    const float cc = round_bf16(__fmul_rn(xh, q_pre ? q_c1 : __bfloat162float(cr[d + 64])));
+                    const float dd = round_bf16(__fmul_rn(xl, q_pre ? q_s1 : __bfloat162float(sr[d + 64])));
                     lo = __float2bfloat16_rn(__fadd_rn(a, b));
                     hi = __float2bfloat16_rn(__fadd_rn(cc, dd));
                 } else {
@@ -672,39 +977,40 @@ decode_stack_kernel(const __grid_constant__ StackParams p) {
         dp.layer = li;
         grid_arrive(p.sync, epoch, G);
         if (c < n_items && warp < DWARPS)
-            attn_item<1>(dp, c % p.n_splits, (c / p.n_splits) % Hkv, c / (p.n_splits * Hkv), smem, tid);
+            attn_item<1, FEED ? TK_ATTN_STAGES : DSTAGES>(dp, c % p.n_splits, (c / p.n_splits) % Hkv, c / (p.n_splits * Hkv), smem, tid);
         grid_wait(p.sync, epoch, G);
         MK_TRACE(li, 1, 0);
         MK_GT(li, 3);
         for (int item = c; item < n_items; item += G) {
             const int split = item % p.n_splits, kvh = (item / p.n_splits) % Hkv, b = item / (p.n_splits * Hkv);
             if (warp < DWARPS) {
-                if (item == c) attn_item<2>(dp, split, kvh, b, smem, tid);
-                else attn_item<0>(dp, split, kvh, b, smem, tid);
+                if (item == c) attn_item<2, FEED ? TK_ATTN_STAGES : DSTAGES>(dp, split, kvh, b, smem, tid);
+                else attn_item<0, FEED ? TK_ATTN_STAGES : DSTAGES>(dp, split, kvh, b, smem, tid);
                 MK_TRACE(li, 1, 1);
                 __threadfence();
             }
-            __syncthreads();
+            MK_SYNC();
             MK_TRACE(li, 1, 2);
             if (tid == 0) {
                 const unsigned old = atomicAdd(p.sync + 16 + b * Hkv + kvh, 1u);
                 *s_flag = ((old + 1) % (unsigned)p.n_splits) == 0;
             }
-            __syncthreads();
+            MK_SYNC();
             MK_TRACE(li, 1, 3);
             if (*s_flag) {
                 __threadfence();
                 combine_splits(p, b, kvh);
             }
-            __syncthreads();
+            MK_SYNC();
         }
         MK_TRACE(li, 1, 5);
         MK_GT(li, 5);
+        if (FEED == 1 && tid == 0) *reinterpret_cast<volatile int*>(s_misc_i + 44) = li + 1;   // opens the producer's O gate (dbg bit 3)
         MK_PHASE_DONE();
         grid_arrive(p.sync, epoch, G);
 
         // ---- O projection
-        gemv_phase<NB, 1>(p, smem, wo, Hq * HD, d_r1 - d_r0, d_row,
+        run_gemv<NB, 1, false, FEED>(p, smem, feed, wo, Hq * HD, d_r1 - d_r0, d_row,
             [&] {
                 grid_wait(p.sync, epoch, G);
                 MK_TRACE(li, 2, 1);
@@ -717,7 +1023,7 @@ decode_stack_kernel(const __grid_constant__ StackParams p) {
         grid_arrive(p.sync, epoch, G);
 
         // ---- gate/up: h2 = hn + o; x = RMSNorm(h2); act = silu(x Wg^T) * (x Wu^T)
-        gemv_phase<NB, 2>(p, smem, wgu, D, i_r1 - i_r0, gu_row,
+        run_gemv<NB, 2, true, FEED>(p, smem, feed, wgu, D, i_r1 - i_r0, gu_row,
             [&] {
                 grid_wait(p.sync, epoch, G);
                 MK_TRACE(li, 3, 1);
@@ -734,7 +1040,7 @@ decode_stack_kernel(const __grid_constant__ StackParams p) {
         grid_arrive(p.sync, epoch, G);
 
         // ---- down projection -> pending (added to the residual stream by the next norm)
-        gemv_phase<NB, 1>(p, smem, wd, I, d_r1 - d_r0, d_row,
+        run_gemv<NB, 1, false, FEED>(p, smem, feed, wd, I, d_r1 - d_r0, d_row,
             [&] {
                 grid_wait(p.sync, epoch, G);
                 MK_TRACE(li, 4, 1);
@@ -750,7 +1056,7 @@ decode_stack_kernel(const __grid_constant__ StackParams p) {
     // ---- final norm, lm_head, greedy argmax (ties -> lowest index, as torch.argmax on these logits)
     float best = -INFINITY;
     int best_i = 0x7FFFFFFF;
-    gemv_phase<NB, 1>(p, smem, p.lm_head, D, v_r1 - v_r0, v_row,
+    run_gemv<NB, 1, true, FEED>(p, smem, feed, p.lm_head, D, v_r1 - v_r0, v_row,
         [&] {
             grid_wait(p.sync, epoch, G);
             preamble_norm<NB>(p, smem, hb0, false, p.pending, p.final_norm, nullptr);
@@ -766,11 +1072,11 @@ decode_stack_kernel(const __grid_constant__ StackParams p) {
         pol, p.n_layer, 0);
     {
         // threads with tid % NB == n saw stream n only (MK_THREADS is a multiple of NB)
-        float* red_v = reinterpret_cast<float*>(smem + p.off_misc) + 64;
+        float* red_v = FEED ? reinterpret_cast<float*>(smem + p.off_part) : reinterpret_cast<float*>(smem + p.off_misc) + 64;
         int* red_i = reinterpret_cast<int*>(red_v + MK_THREADS);
         red_v[tid] = best;
         red_i[tid] = best_i;
-        __syncthreads();
+        MK_SYNC();
         if (tid < NB) {
             float bv = -INFINITY;
             int bi = 0x7FFFFFFF;
@@ -796,6 +1102,47 @@ decode_stack_kernel(const __grid_constant__ StackParams p) {
         const unsigned aborted = __ldcg(p.sync + 1);
         p.tok_out[tid] = aborted ? -1 : (bi == 0x7FFFFFFF ? 0 : bi);
     }
+}
+
+// one thread per 16 bytes of a weight matrix: where does it go in the packed stream?
+__global__ void __launch_bounds__(256)
+tk_pack_kernel(const int4* __restrict__ W, int N, int K, int ph, int li, const TkDims d, unsigned char* __restrict__ out) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int K8 = K >> 3;
+    if (idx >= (long long)N * K8) return;
+    const int r = (int)(idx / K8), kc = (int)(idx % K8);
+    const TkPhase P = tk_phase(d, ph);
+    int unit = r, which = 0;
+    if (ph == 0) {
+        const int h = r >> 7, dd = r & 127;
+        which = dd >> 6;
+        unit = h * 64 + (dd & 63);
+    } else if (ph == 2) {
+        which = r >= d.I ? 1 : 0;
+        unit = which ? r - d.I : r;
+    }
+    const int c = tk_owner(unit, P.n_total, d.G);
+    const int u0 = tk_lo(P.n_total, c, d.G), nu = tk_lo(P.n_total, c + 1, d.G) - u0;
+    const int ul = unit - u0;
+    const int ng = tk_groups(nu, P.rpu, P.wide);
+    const int gi = tk_owner(ul, nu, ng);
+    const int g0 = tk_lo(nu, gi, ng), g1 = tk_lo(nu, gi + 1, ng);
+    const int rows = (g1 - g0) * P.rpu, rg = (ul - g0) * P.rpu + which;
+    const int KS = tk_ks(rows, P.wide);
+    const int s = kc >> 2, t = kc & 3, stage = s / KS, s_in = s % KS;
+    const long long layer_bytes = tk_layer_before(d, c + 1) - tk_layer_before(d, c);
+    long long off = tk_cta_base(d, c);
+    if (ph < 4) {
+        off += (long long)li * layer_bytes;
+        for (int q = 0; q < ph; ++q) {
+            const TkPhase Q = tk_phase(d, q);
+            off += (long long)(tk_lo(Q.n_total, c + 1, d.G) - tk_lo(Q.n_total, c, d.G)) * Q.rpu * Q.K * 2;
+        }
+    } else {
+        off += (long long)d.n_layer * layer_bytes;
+    }
+    off += (long long)g0 * P.rpu * K * 2 + (long long)stage * KS * rows * 64 + ((long long)s_in * rows + rg) * 64 + t * 16;
+    *reinterpret_cast<int4*>(out + off) = __ldg(W + idx);
 }
 
 static size_t ws_align(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -891,6 +1238,50 @@ int svln_decode_stack_trace(long long* host, int max_entries) {
     return n;
 }
 
+static TkDims tk_dims(const svln_decode_stack* d, int G) {
+    return TkDims{d->n_layer, d->hidden, d->inter, d->n_q_head, d->n_kv_head, d->vocab, G};
+}
+
+size_t svln_decode_stack_packed_bytes(const svln_decode_stack* d) {
+    if (!d || d->n_layer < 1 || d->hidden < 32 || d->inter < 32 || d->n_q_head < 1 || d->n_kv_head < 1 || d->vocab < 1 ||
+        d->head_dim != HD) return 0;
+    const int G = stack_grid();
+    return (size_t)tk_cta_base(tk_dims(d, G), G);
+}
+
+int svln_decode_stack_pack(const svln_decode_stack* d, void* packed, size_t packed_bytes, svln_stream_t stream) {
+    SVLN_REQUIRE(d && packed && d->layer_ptrs && d->lm_head, SVLN_ERR_INVALID, "svln_decode_stack_pack: null pointer");
+    SVLN_REQUIRE(d->head_dim == HD && d->hidden % 32 == 0 && d->inter % 32 == 0 && d->hidden <= 4096, SVLN_ERR_INVALID,
+                 "svln_decode_stack_pack: hidden/inter must be multiples of 32 (hidden <= 4096), head_dim 128");
+    SVLN_REQUIRE((long long)d->vocab * stack_grid() < (1ll << 31) && (long long)d->inter * stack_grid() < (1ll << 31), SVLN_ERR_RANGE,
+                 "svln_decode_stack_pack: vocab / inter too large for the 32-bit row partition");
+    const size_t need = svln_decode_stack_packed_bytes(d);
+    SVLN_REQUIRE(need > 0 && packed_bytes >= need, SVLN_ERR_NOMEM, "svln_decode_stack_pack: %zu < %zu bytes", packed_bytes, need);
+    SVLN_REQUIRE(((uintptr_t)packed & 127) == 0, SVLN_ERR_INVALID, "svln_decode_stack_pack: destination not 128-byte aligned");
+    const int G = stack_grid();
+    const TkDims dims = tk_dims(d, G);
+    cudaStream_t st = (cudaStream_t)stream;
+    std::vector<long long> ptrs((size_t)d->n_layer * 8);
+    SVLN_CUDA(cudaMemcpyAsync(ptrs.data(), d->layer_ptrs, ptrs.size() * sizeof(long long), cudaMemcpyDeviceToHost, st));
+    SVLN_CUDA(cudaStreamSynchronize(st));
+    auto pack = [&](const void* W, int ph, int li) {
+        const TkPhase P = tk_phase(dims, ph);
+        const long long n16 = (long long)P.n_total * P.rpu * (P.K >> 3);
+        tk_pack_kernel<<<(unsigned)((n16 + 255) / 256), 256, 0, st>>>((const int4*)W, P.n_total * P.rpu, P.K, ph, li, dims,
+                                                                     (unsigned char*)packed);
+    };
+    for (int li = 0; li < d->n_layer; ++li) {
+        const long long* L = ptrs.data() + (size_t)li * 8;
+        SVLN_REQUIRE(L[0] && L[2] && L[3] && L[4], SVLN_ERR_INVALID, "svln_decode_stack_pack: null weight pointer in layer %d", li);
+        pack((const void*)L[0], 0, li);
+        pack((const void*)L[2], 1, li);
+        pack((const void*)L[3], 2, li);
+        pack((const void*)L[4], 3, li);
+    }
+    pack(d->lm_head, 4, 0);
+    return check_launch("tk_pack_kernel");
+}
+
 int svln_decode_stack_step(const svln_kv_arena* arena, const svln_decode_stack* d, svln_stream_t stream) {
     int rc = stack_check(arena, d, "svln_decode_stack_step");
     if (rc) return rc;
@@ -931,8 +1322,22 @@ int svln_decode_stack_step(const svln_kv_arena* arena, const svln_decode_stack* 
     p.off_ring = (int)align_up((size_t)p.off_rowmap + (MK_CAP + MK_CAP / 16 + 2) * 4, 128);
     size_t misc = (size_t)p.off_ring + (size_t)MK_RING_SLOTS * MK_THREADS * 16;
     if (misc < (size_t)DEC_SMEM) misc = DEC_SMEM;
+    static const int feed_env = getenv("SVLN_STACK_FEED") ? atoi(getenv("SVLN_STACK_FEED")) : 1;
+    const bool packed_feed = d->packed != nullptr && feed_env != 0;
+    p.packed = packed_feed ? (const unsigned char*)d->packed : nullptr;
+    if (packed_feed) {
+        // x and the partial sums share the attention item's 96 KB; the stage ring sits behind it, so the producer
+        // may fill it whatever the compute warps are doing
+        SVLN_REQUIRE(d->packed_bytes >= svln_decode_stack_packed_bytes(d), SVLN_ERR_NOMEM,
+                     "svln_decode_stack_step: packed stream %zu < %zu bytes", d->packed_bytes, svln_decode_stack_packed_bytes(d));
+        size_t ring = align_up((size_t)p.off_part + (size_t)MK_WARPS * TK_WIDE_ROWS * B * 4, 1024);
+        if (ring < (size_t)TK_ATTN_SMEM) ring = TK_ATTN_SMEM;
+        p.off_ring = (int)ring;
+        misc = ring + (size_t)TK_SLOTS * TK_SLOT_BYTES;
+    }
     p.off_misc = (int)misc;
-    const size_t smem = misc + MK_MISC;
+    static const int pad_env = getenv("SVLN_STACK_SMEM_PAD") ? atoi(getenv("SVLN_STACK_SMEM_PAD")) : 0;   // experiment: shrink L1
+    const size_t smem = misc + (packed_feed ? TK_MISC : MK_MISC) + (size_t)pad_env;
     SVLN_REQUIRE(smem <= 227 * 1024, SVLN_ERR_RANGE, "svln_decode_stack_step: %zu bytes of shared memory needed", smem);
     static const int stop_env = getenv("SVLN_STACK_STOP") ? atoi(getenv("SVLN_STACK_STOP")) : 0;
     p.stop_after = stop_env;
@@ -940,19 +1345,19 @@ int svln_decode_stack_step(const svln_kv_arena* arena, const svln_decode_stack* 
     p.dbg = dbg_env;
     static long long* trace_buf = nullptr;
     if (getenv("SVLN_STACK_TRACE") && !trace_buf) {
-        SVLN_CUDA(cudaMalloc(&trace_buf, ((size_t)(p.n_layer + 1) * 6 * 8 + 8 + 160 * 16) * sizeof(long long)));
-        SVLN_CUDA(cudaMemset(trace_buf, 0, ((size_t)(p.n_layer + 1) * 6 * 8 + 8 + 160 * 16) * sizeof(long long)));
+        SVLN_CUDA(cudaMalloc(&trace_buf, ((size_t)(p.n_layer + 1) * 6 * 8 + 8 + 160 * 16 + 4096) * sizeof(long long)));
+        SVLN_CUDA(cudaMemset(trace_buf, 0, ((size_t)(p.n_layer + 1) * 6 * 8 + 8 + 160 * 16 + 4096) * sizeof(long long)));
     }
     p.trace = trace_buf;
     g_trace_dev = trace_buf;
-    g_trace_n = (p.n_layer + 1) * 6 * 8 + 8 + 160 * 16;
+    g_trace_n = (p.n_layer + 1) * 6 * 8 + 8 + 160 * 16 + 4096;
     static const int coop = getenv("SVLN_STACK_COOP") ? atoi(getenv("SVLN_STACK_COOP")) : 1;
 
     cudaStream_t st = (cudaStream_t)stream;
     SVLN_CUDA(cudaMemsetAsync(p.sync, 0, 64 * 4, st));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(G);
-    cfg.blockDim = dim3(MK_THREADS);
+    cfg.blockDim = dim3(MK_THREADS + (packed_feed ? 32 : 0));
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -960,15 +1365,17 @@ int svln_decode_stack_step(const svln_kv_arena* arena, const svln_decode_stack* 
     attr[0].val.cooperative = 1;
     cfg.attrs = attr;
     cfg.numAttrs = coop ? 1 : 0;
-    static size_t smem_set[64] = {0};      // per device: function attributes do not carry over to another GPU
+    static size_t smem_set[2][64] = {{0}};  // per device: function attributes do not carry over to another GPU
     int dev_i = 0;
     SVLN_CUDA(cudaGetDevice(&dev_i));
     dev_i = dev_i < 0 || dev_i >= 64 ? 0 : dev_i;
-    if (smem > smem_set[dev_i]) {
-        SVLN_CUDA(cudaFuncSetAttribute(decode_stack_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        smem_set[dev_i] = smem;
+    if (smem > smem_set[packed_feed][dev_i]) {
+        if (packed_feed) SVLN_CUDA(cudaFuncSetAttribute(decode_stack_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        else SVLN_CUDA(cudaFuncSetAttribute(decode_stack_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_set[packed_feed][dev_i] = smem;
     }
-    SVLN_CUDA(cudaLaunchKernelEx(&cfg, decode_stack_kernel<1>, p));
+    if (packed_feed) SVLN_CUDA(cudaLaunchKernelEx(&cfg, decode_stack_kernel<1, 1>, p));
+    else SVLN_CUDA(cudaLaunchKernelEx(&cfg, decode_stack_kernel<1, 0>, p));
     return check_launch("decode_stack_kernel");
 }
 

@@ -406,6 +406,21 @@ class Qwen2Engine:
         kv_per_tok = 2 * cfg.num_hidden_layers * cfg.num_key_value_heads * cfg.head_dim * 2
         return float(self._stack_weight_bytes + kv_per_tok * kv_len)
 
+    def _stack_packed(self, d) -> Optional[torch.Tensor]:
+        """The packed weight stream of the fused decode step (svln_decode_stack_pack): a second copy of the layer linears
+        and lm_head, one contiguous stream per CTA in consumption order, fed to shared memory by bulk copies.  Built once
+        per engine (weights are immutable after load); SVLN_STACK_FEED=0 keeps the row-major feed and saves the memory."""
+        if os.environ.get("SVLN_STACK_FEED", "1") == "0":
+            return None
+        if getattr(self, "_packed", None) is None:
+            n = self.lib.svln_decode_stack_packed_bytes(C.byref(d))
+            if n == 0:
+                raise _lib.SvlnError(-22, "svln_decode_stack_packed_bytes rejected the descriptor")
+            buf = torch.empty(n, dtype=torch.uint8, device=self.device)
+            check(self.lib.svln_decode_stack_pack(C.byref(d), buf.data_ptr(), n, cur_stream()))
+            self._packed = buf
+        return self._packed
+
     def _stack_desc(self, state: "_DecodeState", tok: torch.Tensor):
         """svln_decode_stack descriptor bound to this state's device tensors (built once per state)."""
         if state.stack is None:
@@ -425,6 +440,8 @@ class Qwen2Engine:
                                   if self.keep_decode_logits else None)
             d.tok_in, d.tok_out, d.logits = state.stack_tok_in.data_ptr(), state.stack_tok_out.data_ptr(), ptr(state.stack_logits)
             d.seq_env, d.kv_len = state.seq_env.data_ptr(), state.kv_len.data_ptr()
+            packed = self._stack_packed(d)
+            d.packed, d.packed_bytes = (packed.data_ptr(), packed.numel()) if packed is not None else (None, 0)
             nbytes = self.lib.svln_decode_stack_workspace_bytes(C.byref(d))
             if nbytes == 0:
                 raise _lib.SvlnError(-22, "svln_decode_stack_workspace_bytes rejected the descriptor")
