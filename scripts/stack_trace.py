@@ -49,6 +49,8 @@ print(f"barrier qkv->attn {qkv_to_attn:.0f}; attention work (CTA 0) {attn:.0f}: 
 tot += qkv_to_attn + attn
 layer = (t[3:L - 1, 0, 0] - t[2:L - 2, 0, 0]).mean()
 print(f"sum {tot:.0f}; layer period {layer:.0f} cycles; whole step {(t[L,0,5]-t[0,0,0]):.0f} cycles")
+pn = t[L, 5, :5]
+print("norm preamble (last one traced, CTA 0 thread 0): loads+sumsq %.0f, sync %.0f, scale+store %.0f, sync %.0f" % tuple(pn[i + 1] - pn[i] for i in range(4)))
 print("attention item (last layer, CTA 0): q loads issued %.0f, first tile landed %.0f, tiles done %.0f, merge staged %.0f, partial written %.0f" %
       tuple(ad[i] - ad[0] for i in range(1, 6)))
 

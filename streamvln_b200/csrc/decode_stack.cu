@@ -397,19 +397,34 @@ __device__ __forceinline__ void gemv_phase(const StackParams& p, unsigned char* 
     MK_GT(tr_li, tr_ph * 3 + 2);
 }
 
-// x = RMSNorm(src (+ add)) * w for every stream into shared memory; CTA 0 also stores the summed residual stream.
-// src_embed: rows are looked up in the embedding table by token id (layer 0), else src is [NB][D].
+// The RMSNorm weights of a phase do not depend on this step: every thread fetches its share BEFORE the grid barrier is
+// waited for (they come from HBM - 14 GB of weights have passed through L2 since their last use).
+constexpr int MK_NORM_Q = 2;  // D <= 256 * 2 * 8 = 4096
+struct NormW { int4 w[MK_NORM_Q]; };
+__device__ __forceinline__ NormW norm_w_load(const StackParams& p, const __nv_bfloat16* lnw) {
+    NormW r;
+    const int D8 = p.D >> 3;
+#pragma unroll
+    for (int q = 0; q < MK_NORM_Q; ++q) {
+        const int c = q * MK_THREADS + threadIdx.x;
+        r.w[q] = c < D8 ? __ldg(reinterpret_cast<const int4*>(lnw) + c) : make_int4(0, 0, 0, 0);
+    }
+    return r;
+}
+
+// x = RMSNorm(src) * w for every stream into shared memory.  src is the residual stream [NB][D] (summed by the
+// epilogues of the O and down projections), or the embedding rows of the step's tokens (layer 0).
 template <int NB>
 __device__ __forceinline__ void preamble_norm(const StackParams& p, unsigned char* smem, const __nv_bfloat16* src,
-                                           bool src_embed, const __nv_bfloat16* add, const __nv_bfloat16* lnw,
-                                           __nv_bfloat16* h_out) {
+                                           bool src_embed, const NormW& lw) {
     __nv_bfloat16* xs = reinterpret_cast<__nv_bfloat16*>(smem);
     float* red = reinterpret_cast<float*>(smem + p.off_misc);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int D8 = p.D >> 3;
-    constexpr int MAXQ = 2;  // D <= 256 * 2 * 8 = 4096
-    int4 v[NB][MAXQ], a[NB][MAXQ], wv[MAXQ];
-    // every load first (one L2 round trip), arithmetic after
+    constexpr int MAXQ = MK_NORM_Q;
+    int4 v[NB][MAXQ];
+    long long* pt = (p.trace && blockIdx.x == 0 && tid == 0 && !src_embed) ? p.trace + ((int64_t)p.n_layer * 6 + 5) * 8 : nullptr;
+    if (pt) pt[0] = clock64();
 #pragma unroll
     for (int n = 0; n < NB; ++n) {
         const int4* s;
@@ -423,16 +438,8 @@ __device__ __forceinline__ void preamble_norm(const StackParams& p, unsigned cha
 #pragma unroll
         for (int q = 0; q < MAXQ; ++q) {
             const int c = q * MK_THREADS + tid;
-            if (c < D8) {
-                v[n][q] = src_embed ? __ldg(s + c) : __ldcg(s + c);
-                if (add) a[n][q] = __ldcg(reinterpret_cast<const int4*>(add + (int64_t)n * p.D) + c);
-            }
+            if (c < D8) v[n][q] = src_embed ? __ldg(s + c) : __ldcg(s + c);
         }
-    }
-#pragma unroll
-    for (int q = 0; q < MAXQ; ++q) {
-        const int c = q * MK_THREADS + tid;
-        if (c < D8) wv[q] = __ldg(reinterpret_cast<const int4*>(lnw) + c);
     }
 #pragma unroll
     for (int n = 0; n < NB; ++n) {
@@ -441,17 +448,7 @@ __device__ __forceinline__ void preamble_norm(const StackParams& p, unsigned cha
         for (int q = 0; q < MAXQ; ++q) {
             const int c = q * MK_THREADS + tid;
             if (c < D8) {
-                uint32_t* u = reinterpret_cast<uint32_t*>(&v[n][q]);
-                if (add) {
-                    const uint32_t* ru = reinterpret_cast<const uint32_t*>(&a[n][q]);
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const float a0 = bf16_bits_to_f32(u[k] & 0xFFFFu) + bf16_bits_to_f32(ru[k] & 0xFFFFu);
-                        const float a1 = bf16_bits_to_f32(u[k] >> 16) + bf16_bits_to_f32(ru[k] >> 16);
-                        u[k] = f32_to_bf16_bits(a0) | (f32_to_bf16_bits(a1) << 16);
-                    }
-                }
-                if (h_out && blockIdx.x == 0) reinterpret_cast<int4*>(h_out + (int64_t)n * p.D)[c] = v[n][q];
+                const uint32_t* u = reinterpret_cast<const uint32_t*>(&v[n][q]);
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     const float a0 = bf16_bits_to_f32(u[k] & 0xFFFFu), a1 = bf16_bits_to_f32(u[k] >> 16);
@@ -462,7 +459,9 @@ __device__ __forceinline__ void preamble_norm(const StackParams& p, unsigned cha
         ss = warp_sum(ss);
         if (lane == 0) red[n * MK_WARPS + warp] = ss;
     }
+    if (pt) pt[1] = clock64();
     MK_SYNC();
+    if (pt) pt[2] = clock64();
 #pragma unroll
     for (int n = 0; n < NB; ++n) {
         float tot = 0.f;
@@ -473,7 +472,7 @@ __device__ __forceinline__ void preamble_norm(const StackParams& p, unsigned cha
         for (int q = 0; q < MAXQ; ++q) {
             const int c = q * MK_THREADS + tid;
             if (c < D8) {
-                const uint32_t* wu = reinterpret_cast<const uint32_t*>(&wv[q]);
+                const uint32_t* wu = reinterpret_cast<const uint32_t*>(&lw.w[q]);
                 const uint32_t* u = reinterpret_cast<const uint32_t*>(&v[n][q]);
                 int4 o;
                 uint32_t* ou = reinterpret_cast<uint32_t*>(&o);
@@ -489,7 +488,9 @@ __device__ __forceinline__ void preamble_norm(const StackParams& p, unsigned cha
             }
         }
     }
+    if (pt) pt[3] = clock64();
     MK_SYNC();
+    if (pt) pt[4] = clock64();
 }
 
 // x = src[NB][K] (written earlier in this launch by other CTAs) into shared memory, 8 loads in flight per thread
@@ -932,10 +933,11 @@ decode_stack_kernel(const __grid_constant__ StackParams p) {
                         q_c1 = __bfloat162float(cr[d + 64]); q_s1 = __bfloat162float(sr[d + 64]);
                     }
                 }
+                const NormW lw = norm_w_load(p, ln1);
                 if (li > 0) grid_wait(p.sync, epoch, G);     // previous layer's down projection
                 MK_TRACE(li, 0, 1);
                 MK_GT(li, 0);
-                if (!(p.dbg & 1)) preamble_norm<NB>(p, smem, hb0, li == 0, li == 0 ? nullptr : p.pending, ln1, hb1);
+                if (!(p.dbg & 1)) preamble_norm<NB>(p, smem, hb0, li == 0, lw);
             },
             [&](int u, int n, const float (&s)[2]) {
                 const int pr = qkv_p0 + u, h = pr >> 6, d = pr & 63;
@@ -1010,14 +1012,28 @@ decode_stack_kernel(const __grid_constant__ StackParams p) {
         grid_arrive(p.sync, epoch, G);
 
         // ---- O projection
+        // the epilogue adds the projection to the residual stream: hb1 = resid_in + o (HF: hidden = residual + attn).
+        // resid_in = hb0, or the token's embedding row in layer 0; this thread's element is fetched before the barrier.
+        const bool r_pre = NB == 1 && d_r1 - d_r0 <= 32;
+        float r_val = 0.f;
+        auto resid_in = [&](int n, int row) {
+            if (li > 0) return __bfloat162float(__ldcg(hb0 + (int64_t)n * D + row));
+            int64_t tok = p.tok_in[n];
+            tok = tok < 0 ? 0 : (tok >= p.V ? p.V - 1 : tok);
+            return __bfloat162float(p.embed[tok * D + row]);
+        };
         run_gemv<NB, 1, false, FEED>(p, smem, feed, wo, Hq * HD, d_r1 - d_r0, d_row,
             [&] {
+                if (r_pre && tid < d_r1 - d_r0) r_val = resid_in(0, d_r0 + tid);
                 grid_wait(p.sync, epoch, G);
                 MK_TRACE(li, 2, 1);
                 MK_GT(li, 6);
                 preamble_copy<NB>(p, smem, p.attn_out, Hq * HD);
             },
-            [&](int u, int n, const float (&s)[1]) { p.o[(int64_t)n * D + d_r0 + u] = __float2bfloat16_rn(s[0]); },
+            [&](int u, int n, const float (&s)[1]) {
+                const float r = r_pre ? r_val : resid_in(n, d_r0 + u);
+                hb1[(int64_t)n * D + d_r0 + u] = __float2bfloat16_rn(r + round_bf16(s[0]));
+            },
             pol, li, 2);
         MK_PHASE_DONE();
         grid_arrive(p.sync, epoch, G);
@@ -1025,10 +1041,11 @@ decode_stack_kernel(const __grid_constant__ StackParams p) {
         // ---- gate/up: h2 = hn + o; x = RMSNorm(h2); act = silu(x Wg^T) * (x Wu^T)
         run_gemv<NB, 2, true, FEED>(p, smem, feed, wgu, D, i_r1 - i_r0, gu_row,
             [&] {
+                const NormW lw = norm_w_load(p, ln2);
                 grid_wait(p.sync, epoch, G);
                 MK_TRACE(li, 3, 1);
                 MK_GT(li, 9);
-                preamble_norm<NB>(p, smem, hb1, false, p.o, ln2, hb0);
+                preamble_norm<NB>(p, smem, hb1, false, lw);
             },
             [&](int u, int n, const float (&s)[2]) {
                 const float gv = round_bf16(s[0]), uv = round_bf16(s[1]);
@@ -1039,15 +1056,20 @@ decode_stack_kernel(const __grid_constant__ StackParams p) {
         MK_PHASE_DONE();
         grid_arrive(p.sync, epoch, G);
 
-        // ---- down projection -> pending (added to the residual stream by the next norm)
+        // ---- down projection; the epilogue closes the layer's residual stream: hb0 = hb1 + mlp (HF: residual + mlp)
+        float m_val = 0.f;
         run_gemv<NB, 1, false, FEED>(p, smem, feed, wd, I, d_r1 - d_r0, d_row,
             [&] {
+                if (r_pre && tid < d_r1 - d_r0) m_val = __bfloat162float(__ldcg(hb1 + d_r0 + tid));   // written two barriers ago
                 grid_wait(p.sync, epoch, G);
                 MK_TRACE(li, 4, 1);
                 MK_GT(li, 12);
                 preamble_copy<NB>(p, smem, p.act, I);
             },
-            [&](int u, int n, const float (&s)[1]) { p.pending[(int64_t)n * D + d_r0 + u] = __float2bfloat16_rn(s[0]); },
+            [&](int u, int n, const float (&s)[1]) {
+                const float r = r_pre ? m_val : __bfloat162float(__ldcg(hb1 + (int64_t)n * D + d_r0 + u));
+                hb0[(int64_t)n * D + d_r0 + u] = __float2bfloat16_rn(r + round_bf16(s[0]));
+            },
             pol, li, 4);
         MK_PHASE_DONE();
         grid_arrive(p.sync, epoch, G);
@@ -1058,8 +1080,9 @@ decode_stack_kernel(const __grid_constant__ StackParams p) {
     int best_i = 0x7FFFFFFF;
     run_gemv<NB, 1, true, FEED>(p, smem, feed, p.lm_head, D, v_r1 - v_r0, v_row,
         [&] {
+            const NormW lw = norm_w_load(p, p.final_norm);
             grid_wait(p.sync, epoch, G);
-            preamble_norm<NB>(p, smem, hb0, false, p.pending, p.final_norm, nullptr);
+            preamble_norm<NB>(p, smem, hb0, false, lw);
         },
         [&](int u, int n, const float (&s)[1]) {
             // HF's lm_head is a bf16 Linear upcast with .float(): the greedy pick (and its lowest-index tie-break)
