@@ -87,7 +87,7 @@ __device__ __forceinline__ void group_sync() {
     else asm volatile("bar.sync %0, %1;" ::"n"(BAR_ID), "n"(DWARPS * 32) : "memory");
 }
 // (q may have been written earlier in the same kernel by another CTA - fused decode stack - so it is read
-// through L2 with __ldcg, never through the non-coherent path)
+// through L2 with ld.global.cg (volatile asm), never through the non-coherent path)
 
 // One (split, kv head, row group) work item, executed by DWARPS*32 threads that share barrier BAR_ID
 // (0 = the whole CTA, i.e. __syncthreads; other ids let a 4-warp group of a larger CTA run it).
@@ -171,8 +171,8 @@ __device__ __forceinline__ void attn_decode_body(const DecodeParams& p, int spli
         const uint32_t* qrow = reinterpret_cast<const uint32_t*>(p.q + ((int64_t)(qs + tq) * p.n_q_head + hq) * HD);
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks) {
-            qa[ks][h] = valid ? __ldcg(qrow + ks * 8 + tig) : 0u;          // cols ks*16 + 2*tig
-            qa[ks][h + 2] = valid ? __ldcg(qrow + ks * 8 + 4 + tig) : 0u;  // cols ks*16 + 8 + 2*tig
+            qa[ks][h] = valid ? ld_cg_u32(qrow + ks * 8 + tig) : 0u;          // cols ks*16 + 2*tig
+            qa[ks][h + 2] = valid ? ld_cg_u32(qrow + ks * 8 + 4 + tig) : 0u;  // cols ks*16 + 8 + 2*tig
         }
     }
 

@@ -438,7 +438,7 @@ __device__ __forceinline__ void preamble_norm(const StackParams& p, unsigned cha
 #pragma unroll
         for (int q = 0; q < MAXQ; ++q) {
             const int c = q * MK_THREADS + tid;
-            if (c < D8) v[n][q] = src_embed ? __ldg(s + c) : __ldcg(s + c);
+            if (c < D8) v[n][q] = src_embed ? __ldg(s + c) : ld_cg_v4(s + c);
         }
     }
 #pragma unroll
@@ -504,7 +504,7 @@ __device__ __forceinline__ void preamble_copy(const StackParams& p, unsigned cha
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
             const int c = base + u * MK_THREADS + threadIdx.x;
-            if (c < total) tmp[u] = __ldcg(s4 + c);
+            if (c < total) tmp[u] = ld_cg_v4(s4 + c);
         }
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
@@ -525,10 +525,10 @@ __device__ __noinline__ void combine_splits(const StackParams& p, int b, int kvh
     const int g = p.Hq / p.Hkv;
     const int64_t slot0 = ((int64_t)b * p.Hkv + kvh) * p.n_splits;
     for (int r = warp; r < g; r += MK_WARPS) {
-        const float ms = lane < p.n_splits ? __ldcg(p.part_m + (slot0 + lane) * DROWS + r) : -INFINITY;
+        const float ms = lane < p.n_splits ? ld_cg_f(p.part_m + (slot0 + lane) * DROWS + r) : -INFINITY;
         const float m = warp_max(ms);
         const float w = (lane < p.n_splits && ms != -INFINITY) ? exp2f((ms - m) * p.scale_log2) : 0.f;
-        float l = lane < p.n_splits ? __ldcg(p.part_l + (slot0 + lane) * DROWS + r) * w : 0.f;
+        float l = lane < p.n_splits ? ld_cg_f(p.part_l + (slot0 + lane) * DROWS + r) * w : 0.f;
         l = warp_sum(l);
         const float4* po = reinterpret_cast<const float4*>(p.part_o + (slot0 * DROWS + r) * HD) + lane;
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -536,7 +536,7 @@ __device__ __noinline__ void combine_splits(const StackParams& p, int b, int kvh
             float4 v[16];
 #pragma unroll
             for (int u = 0; u < 16; ++u)
-                if (s0 + u < p.n_splits) v[u] = __ldcg(po + (int64_t)(s0 + u) * (DROWS * HD / 4));
+                if (s0 + u < p.n_splits) v[u] = ld_cg_f4(po + (int64_t)(s0 + u) * (DROWS * HD / 4));
 #pragma unroll
             for (int u = 0; u < 16; ++u) {
                 const float ws = __shfl_sync(0xffffffffu, w, (s0 + u) & 31);
@@ -576,6 +576,9 @@ __device__ __noinline__ void attn_item(const DecodeParams& dp, int split, int kv
 // Rows of a CTA are taken in balanced groups of <= 32 rows (QKV, O, down: the 8 warps interleave over the k32-steps
 // of a stage, as in the LDGSTS variant) or <= 256 rows (gate/up, lm_head: one k32-step fills a stage, warp w owns row
 // blocks w and w + 8 and sweeps every k-step itself: no cross-warp sum).
+#ifndef TK_XCOPY
+#define TK_XCOPY 3            // bit 0: x of the O projection by bulk copy, bit 1: x of the down projection
+#endif
 constexpr int TK_SLOT_BYTES = 32768;
 constexpr int TK_SLOTS = 3;
 constexpr int TK_ATTN_STAGES = 2;                  // K/V tile stages of the in-kernel attention item: 64 KB
@@ -627,7 +630,7 @@ __host__ __device__ inline long long tk_cta_base(const TkDims& d, int c) {
     return (long long)d.n_layer * tk_layer_before(d, c) + (long long)tk_lo(d.V, c, d.G) * d.D * 2;
 }
 
-struct TkFeed { uint32_t ring, full, empty; unsigned slot, par; unsigned* sync; const int* gate; };
+struct TkFeed { uint32_t ring, full, empty; unsigned slot, par; unsigned* sync; const int* gate; uint32_t xbar; };
 
 __device__ __forceinline__ void tk_mbar_init(uint32_t bar, int count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
@@ -821,6 +824,23 @@ __device__ __forceinline__ void gemv_phase_tk(const StackParams& p, unsigned cha
     MK_GT(tr_li, tr_ph * 3 + 2);
 }
 
+// x = src[K] (written earlier in this launch by other CTAs) into shared memory with ONE bulk copy issued by thread 0
+// (packed-feed variant, one stream): a single L2 round trip instead of two rounds of 8 LDG + 8 STS per thread.
+// x = src[K] (written earlier in this launch by other CTAs) into shared memory with ONE bulk copy issued by thread 0
+// (packed-feed variant, one stream): a single L2 round trip instead of two rounds of 8 LDG + 8 STS per thread.
+__device__ __forceinline__ void preamble_copy_tk(const StackParams& p, unsigned char* smem, const TkFeed& f, uint32_t bar, uint32_t parity,
+                                                 const __nv_bfloat16* src, int K) {
+    if (threadIdx.x == 0) {
+        // src was written through the generic proxy by other SMs (ordered before us by their fence + the grid barrier's
+        // acquire); the bulk copy reads through the async proxy: a proxy fence in between
+        asm volatile("fence.proxy.async.global;" ::: "memory");
+        tk_mbar_expect(bar, (uint32_t)K * 2);
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(smem_u32(smem)), "l"(src), "r"((uint32_t)K * 2), "r"(bar) : "memory");
+    }
+    tk_mbar_wait(bar, parity, f.sync);      // every thread waits itself: the bytes are then visible to it
+}
+
 template <int NB, int RPU, bool WIDE, int FEED, class RowFn, class MidFn, class EpiFn>
 __device__ __forceinline__ void run_gemv(const StackParams& p, unsigned char* smem, TkFeed& feed, const __nv_bfloat16* W,
                                          int K, int n_units, RowFn rowfn, MidFn mid, EpiFn epi, uint64_t pol, int tr_li,
@@ -846,12 +866,15 @@ decode_stack_kernel(const __grid_constant__ StackParams p) {
     int* s_nq = s_misc_i + 40;      // [NB]
     if (tid < NB) { s_qstart[tid] = tid; s_nq[tid] = 1; }
     if (tid == 0) s_misc_i[44] = 0;
-    TkFeed feed = {0, 0, 0, 0, 0, p.sync, s_misc_i + 44};
+    TkFeed feed = {0, 0, 0, 0, 0, p.sync, s_misc_i + 44, 0};
     if constexpr (FEED == 1) {
         feed.ring = smem_u32(smem + p.off_ring);
         feed.full = smem_u32(smem + p.off_misc + TK_BAR_OFF);
         feed.empty = feed.full + TK_SLOTS * 8;
+        feed.xbar = feed.empty + TK_SLOTS * 8;
         if (tid == 0) {
+            tk_mbar_init(feed.xbar, 1);          // x of the O projection, one use per layer: parity = layer & 1
+            tk_mbar_init(feed.xbar + 8, 1);      // x of the down projection
             for (int s = 0; s < TK_SLOTS; ++s) { tk_mbar_init(feed.full + s * 8, 1); tk_mbar_init(feed.empty + s * 8, MK_WARPS); }
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
@@ -1017,18 +1040,20 @@ decode_stack_kernel(const __grid_constant__ StackParams p) {
         const bool r_pre = NB == 1 && d_r1 - d_r0 <= 32;
         float r_val = 0.f;
         auto resid_in = [&](int n, int row) {
-            if (li > 0) return __bfloat162float(__ldcg(hb0 + (int64_t)n * D + row));
+            if (li > 0) return ld_cg_bf16(hb0 + (int64_t)n * D + row);
             int64_t tok = p.tok_in[n];
             tok = tok < 0 ? 0 : (tok >= p.V ? p.V - 1 : tok);
             return __bfloat162float(p.embed[tok * D + row]);
         };
         run_gemv<NB, 1, false, FEED>(p, smem, feed, wo, Hq * HD, d_r1 - d_r0, d_row,
             [&] {
-                if (r_pre && tid < d_r1 - d_r0) r_val = resid_in(0, d_r0 + tid);
                 grid_wait(p.sync, epoch, G);
                 MK_TRACE(li, 2, 1);
                 MK_GT(li, 6);
-                preamble_copy<NB>(p, smem, p.attn_out, Hq * HD);
+                if constexpr (FEED == 1 && NB == 1 && (TK_XCOPY & 1)) preamble_copy_tk(p, smem, feed, feed.xbar, (uint32_t)(li & 1), p.attn_out, Hq * HD);
+                else preamble_copy<NB>(p, smem, p.attn_out, Hq * HD);
+                // requested here, used in the epilogue: the load flies under the main loop
+                if (r_pre && tid < d_r1 - d_r0) r_val = resid_in(0, d_r0 + tid);
             },
             [&](int u, int n, const float (&s)[1]) {
                 const float r = r_pre ? r_val : resid_in(n, d_r0 + u);
@@ -1060,14 +1085,15 @@ decode_stack_kernel(const __grid_constant__ StackParams p) {
         float m_val = 0.f;
         run_gemv<NB, 1, false, FEED>(p, smem, feed, wd, I, d_r1 - d_r0, d_row,
             [&] {
-                if (r_pre && tid < d_r1 - d_r0) m_val = __bfloat162float(__ldcg(hb1 + d_r0 + tid));   // written two barriers ago
                 grid_wait(p.sync, epoch, G);
                 MK_TRACE(li, 4, 1);
                 MK_GT(li, 12);
-                preamble_copy<NB>(p, smem, p.act, I);
+                if constexpr (FEED == 1 && NB == 1 && (TK_XCOPY & 2)) preamble_copy_tk(p, smem, feed, feed.xbar + 8, (uint32_t)(li & 1), p.act, I);
+                else preamble_copy<NB>(p, smem, p.act, I);
+                if (r_pre && tid < d_r1 - d_r0) m_val = ld_cg_bf16(hb1 + d_r0 + tid);
             },
             [&](int u, int n, const float (&s)[1]) {
-                const float r = r_pre ? m_val : __bfloat162float(__ldcg(hb1 + (int64_t)n * D + d_r0 + u));
+                const float r = r_pre ? m_val : ld_cg_bf16(hb1 + (int64_t)n * D + d_r0 + u);
                 hb0[(int64_t)n * D + d_r0 + u] = __float2bfloat16_rn(r + round_bf16(s[0]));
             },
             pol, li, 4);
@@ -1118,11 +1144,11 @@ decode_stack_kernel(const __grid_constant__ StackParams p) {
         float bv = -INFINITY;
         int bi = 0x7FFFFFFF;
         for (int j = 0; j < G; ++j) {
-            const float v = __ldcg(p.best_v + j * NB + tid);
-            const int i = __ldcg(p.best_i + j * NB + tid);
+            const float v = ld_cg_f(p.best_v + j * NB + tid);
+            const int i = (int)ld_cg_u32(p.best_i + j * NB + tid);
             if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
         }
-        const unsigned aborted = __ldcg(p.sync + 1);
+        const unsigned aborted = ld_cg_u32(p.sync + 1);
         p.tok_out[tid] = aborted ? -1 : (bi == 0x7FFFFFFF ? 0 : bi);
     }
 }

@@ -78,4 +78,35 @@ __device__ __forceinline__ float warp_max(float v) {
     return v;
 }
 
+
+// Loads of data that ANOTHER CTA of the same launch produced (read through L2, never L1).  asm volatile: the compiler
+// may neither hoist them out of a loop nor reuse an earlier result - `__ldcg` is a plain (non-volatile) asm in the CUDA
+// headers, and nvcc moved __ldcg(hb0 + row) of the fused decode stack out of its layer loop (profiles/
+// r2_decode_stack_experiments.md): garbage that came and went with unrelated code changes.
+__device__ __forceinline__ int4 ld_cg_v4(const int4* p) {
+    int4 r;
+    asm volatile("ld.global.cg.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
+    return r;
+}
+__device__ __forceinline__ float4 ld_cg_f4(const float4* p) {
+    float4 r;
+    asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p) : "memory");
+    return r;
+}
+__device__ __forceinline__ uint32_t ld_cg_u32(const void* p) {
+    uint32_t r;
+    asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(r) : "l"(p) : "memory");
+    return r;
+}
+__device__ __forceinline__ float ld_cg_f(const float* p) {
+    float r;
+    asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(r) : "l"(p) : "memory");
+    return r;
+}
+__device__ __forceinline__ float ld_cg_bf16(const __nv_bfloat16* p) {
+    unsigned short r;
+    asm volatile("ld.global.cg.u16 %0, [%1];" : "=h"(r) : "l"(p) : "memory");
+    return __uint_as_float((uint32_t)r << 16);
+}
+
 }  // namespace svln

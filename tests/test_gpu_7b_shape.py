@@ -339,3 +339,42 @@ def test_zz_print_logit_error_stats():
     print("\n  case | product vs fp32: row, per-element>=floor | HF bf16 vs fp32: row, per-element | product vs HF bf16: row")
     for what, p_all, p_big, h_all, h_big, ph_all in STATS:
         print(f"  {what:32s} {p_all:.2e} {p_big:.2e} | {h_all:.2e} {h_big:.2e} | {ph_all:.2e}")
+
+
+def test_decode_stack_feeds_agree(svln_lib, cuda):
+    """The two weight feeds of svln_decode_stack_step - the packed stream (bulk copies by a producer thread; default) and
+    the row-major LDGSTS feed (descriptor without `packed`) - are the same arithmetic up to the summation order of the wide
+    phases: logits of three decode steps agree to 1e-2 (each is within the HF tolerance on its own) and pick the same ids.
+    7B widths, 2 layers, contexts 3 / 64 / 700."""
+    import os
+    from streamvln_b200.qwen2 import Chunk, Qwen2Config, Qwen2Engine, Qwen2Weights
+
+    cfg = Qwen2Config(num_hidden_layers=2)
+    w = Qwen2Weights.random(cfg, cuda, seed=0)
+    old = os.environ.get("SVLN_STACK_FEED")
+    try:
+        for n_ctx in (3, 64, 700):
+            outs = []
+            for feed in ("1", "0"):
+                os.environ["SVLN_STACK_FEED"] = feed
+                eng = Qwen2Engine(cfg, w, n_env=1, device=cuda)
+                eng.keep_decode_logits = True
+                emb = (torch.randn(n_ctx, cfg.hidden_size, generator=torch.Generator().manual_seed(1)) * 0.05).bfloat16().to(cuda)
+                tok = eng.forward(emb, [Chunk(0, 0, n_ctx, n_ctx)]).argmax(-1)
+                runner = eng._decode_runner([0], False)
+                lg = []
+                for _ in range(3):
+                    tok = runner.step(tok)
+                    lg.append(runner.last_logits().float().clone())
+                runner.finish()
+                outs.append(torch.stack(lg))
+                del eng
+            a, b = outs
+            rel = float((a - b).norm() / b.norm())
+            assert rel <= 1e-2, (n_ctx, rel)
+            assert bool((a.argmax(-1) == b.argmax(-1)).all()), n_ctx
+    finally:
+        if old is None:
+            os.environ.pop("SVLN_STACK_FEED", None)
+        else:
+            os.environ["SVLN_STACK_FEED"] = old

@@ -138,6 +138,22 @@ def test_no_misencoded_ldgsts_in_the_library():
     assert not bad, bad[:3]
 
 
+def test_no_hoistable_coherent_loads_in_the_kernels():
+    """`__ldcg` is a plain, non-volatile asm in the CUDA headers: nvcc may hoist it out of a loop or reuse an earlier result
+    across a grid barrier.  It did, in the fused decode stack (a residual value written by the previous layer was read once,
+    before the layer loop).  Data produced inside a launch is read with the asm-volatile ld_cg_* helpers of svln_common.cuh."""
+    import re
+
+    csrc = Path(__file__).resolve().parent.parent / "streamvln_b200" / "csrc"
+    bad = []
+    for f in sorted(list(csrc.glob("*.cu")) + list(csrc.glob("*.cuh"))):
+        for n, line in enumerate(f.read_text().splitlines(), 1):
+            code = line.split("//")[0]
+            if re.search(r"\b__ldcg\s*\(", code):
+                bad.append(f"{f.name}:{n}")
+    assert not bad, bad
+
+
 def test_decode_stack_abi_argument_checks():
     """svln_decode_stack_* validate their descriptor before touching the device (runs without a GPU): one stream only,
     head_dim 128, matching arena, non-null buffers; errors are negative errno-style codes with a message."""
