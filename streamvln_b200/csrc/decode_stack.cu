@@ -147,8 +147,10 @@ __device__ __forceinline__ void grid_arrive(unsigned* sync, unsigned& epoch, int
     MK_SYNC();
     epoch += (unsigned)G;
     if (threadIdx.x == 0) {
-        __threadfence();
-        atomicAdd(sync, 1u);
+        // release at gpu scope (cumulative over the CTA barrier above): this CTA's stores are performed at L2 before the
+        // count moves.  __threadfence() here is MEMBAR.SC.GPU + CCTL.IVALL - a sequentially consistent fence that also
+        // throws the SM's L1 (spills, stack, read-only tables) away at every barrier.
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(sync) : "memory");
     }
 }
 __device__ __forceinline__ void grid_wait(unsigned* sync, unsigned epoch, int G) {
@@ -156,11 +158,14 @@ __device__ __forceinline__ void grid_wait(unsigned* sync, unsigned epoch, int G)
         unsigned spins = 0;
         for (;;) {
             unsigned v;
-            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(sync) : "memory");
+            // relaxed poll: ld.acquire is LDG + CCTL.IVALL, an L1 flush per poll.  Nothing produced inside the launch is
+            // ever read through L1 (ld_cg_* helpers, cp.async.cg, bulk copies; tests/test_sharding_cpu.py guards it), so
+            // the data the count stands for is read from L2, where the producers' release put it.
+            asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(sync) : "memory");
             if (v >= epoch) break;
             if ((++spins & 1023u) == 0) {
                 unsigned ab;
-                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(ab) : "l"(sync + 1) : "memory");
+                asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(ab) : "l"(sync + 1) : "memory");
                 if (ab != 0) break;
                 if (spins > MK_SPIN_LIMIT) {
                     if (atomicCAS(sync + 1, 0u, epoch / (unsigned)G) == 0u) { sync[2] = blockIdx.x; sync[3] = v; }
@@ -657,7 +662,7 @@ __device__ __forceinline__ void tk_mbar_wait(uint32_t bar, uint32_t parity, unsi
         if (SLEEP_NS > 0) __nanosleep(SLEEP_NS);
         if ((++polls & 4095u) == 0) {
             unsigned ab;
-            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(ab) : "l"(sync + 1) : "memory");
+            asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(ab) : "l"(sync + 1) : "memory");
             if (ab != 0) return;
             if (polls > (1u << 20)) { atomicCAS(sync + 1, 0u, 0x7FFFu); return; }
         }
@@ -1012,20 +1017,19 @@ decode_stack_kernel(const __grid_constant__ StackParams p) {
                 if (item == c) attn_item<2, FEED ? TK_ATTN_STAGES : DSTAGES>(dp, split, kvh, b, smem, tid);
                 else attn_item<0, FEED ? TK_ATTN_STAGES : DSTAGES>(dp, split, kvh, b, smem, tid);
                 MK_TRACE(li, 1, 1);
-                __threadfence();
             }
             MK_SYNC();
             MK_TRACE(li, 1, 2);
             if (tid == 0) {
-                const unsigned old = atomicAdd(p.sync + 16 + b * Hkv + kvh, 1u);
+                // release (cumulative over the CTA barrier): the item's partials are at L2 before the count moves; the CTA
+                // that sees the last count reads them with ld.global.cg (combine_splits)
+                unsigned old;
+                asm volatile("atom.release.gpu.global.add.u32 %0, [%1], 1;" : "=r"(old) : "l"(p.sync + 16 + b * Hkv + kvh) : "memory");
                 *s_flag = ((old + 1) % (unsigned)p.n_splits) == 0;
             }
             MK_SYNC();
             MK_TRACE(li, 1, 3);
-            if (*s_flag) {
-                __threadfence();
-                combine_splits(p, b, kvh);
-            }
+            if (*s_flag) combine_splits(p, b, kvh);
             MK_SYNC();
         }
         MK_TRACE(li, 1, 5);
