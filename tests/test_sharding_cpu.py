@@ -177,6 +177,14 @@ def test_decode_stack_abi_argument_checks():
     assert lib.svln_decode_stack_step(C.byref(arena), C.byref(d), None) == -22
     d.head_dim = 128
     assert lib.svln_decode_stack_step(C.byref(arena), C.byref(d), None) == -22    # null weight / token pointers
+    # the packed weight stream is exactly the layer linears + lm_head, re-laid (no padding bytes), whatever the grid
+    D, I, V, L = 3584, 18944, 152064, 28
+    want = 2 * (L * ((28 + 2 * 4) * 128 * D + D * 28 * 128 + 2 * I * D + D * I) + V * D)
+    assert lib.svln_decode_stack_packed_bytes(C.byref(d)) == want
+    assert lib.svln_decode_stack_pack(C.byref(d), None, want, None) == -22        # null destination / weight table
+    d.head_dim = 64
+    assert lib.svln_decode_stack_packed_bytes(C.byref(d)) == 0
+    d.head_dim = 128
     assert lib.svln_pool_bilinear(None, 1, 27, 14, 3584, None, None) == -22
     assert lib.svln_pool_bilinear(None, 0, 27, 14, 3584, None, None) == 0         # nothing to do
     assert lib.svln_pool_bilinear(None, 1, 27, 14, 3583, None, None) == -22       # dim must be a multiple of 8
