@@ -85,3 +85,15 @@ print("slowest CTAs (mean over 3 steps):", [(int(c), int(gu.mean(0)[c])) for c i
 print("fastest CTAs:", [(int(c), int(gu.mean(0)[c])) for c in order[:8]])
 rel = gu.mean(0) / gu.mean()
 print("relative time quantiles 5/25/50/75/95 %%: " + " ".join("%.3f" % q for q in np.quantile(rel, [0.05, 0.25, 0.5, 0.75, 0.95])))
+
+# ---- attention phase per CTA (layer L // 2): time from its barrier pass to the end of its work, by split index
+n = eng.lib.svln_decode_stack_trace(buf.ctypes.data_as(C.c_void_p), buf.size)
+g = buf[nt + 8:].reshape(160, 16).astype(np.float64)[:G]
+dur = g[:, 5] - g[:, 3]
+passed = g[:, 3] - g[:, 3].min()
+print("attention phase per CTA: ns from barrier pass to work done (CTA = kv head * 32 + split for CTA < 128)")
+for kvh in range(4):
+    row = dur[kvh * 32:(kvh + 1) * 32]
+    print(f"  kv head {kvh}: " + " ".join(f"{int(v / 100):3d}" for v in row) + "   (x100 ns)")
+print("  CTAs 128..147 (no item): " + " ".join(f"{int(v / 100)}" for v in dur[128:]))
+print("barrier pass skew per CTA (x100 ns after the first): " + " ".join(f"{int(v / 100)}" for v in passed))

@@ -412,14 +412,29 @@ class Qwen2Engine:
         per engine (weights are immutable after load); SVLN_STACK_FEED=0 keeps the row-major feed and saves the memory."""
         if os.environ.get("SVLN_STACK_FEED", "1") == "0":
             return None
-        if getattr(self, "_packed", None) is None:
+        cache = self.w.__dict__.setdefault("_packed_streams", {})      # engines that share the weights share the packed copy
+        key = str(self.device)
+        if key not in cache:
             n = self.lib.svln_decode_stack_packed_bytes(C.byref(d))
             if n == 0:
                 raise _lib.SvlnError(-22, "svln_decode_stack_packed_bytes rejected the descriptor")
             buf = torch.empty(n, dtype=torch.uint8, device=self.device)
             check(self.lib.svln_decode_stack_pack(C.byref(d), buf.data_ptr(), n, cur_stream()))
-            self._packed = buf
-        return self._packed
+            cache[key] = buf
+        return cache[key]
+
+    def repack_decode_weights(self) -> None:
+        """Refresh the packed copy after the layer linears or lm_head were changed IN PLACE (the fused decode step reads
+        the packed stream, not the row-major tensors).  The buffer keeps its address, so descriptors and graphs stay valid."""
+        buf = self.w.__dict__.get("_packed_streams", {}).get(str(self.device))
+        if buf is None:
+            return
+        cfg = self.cfg
+        d = _lib.DecodeStackStruct()
+        d.n_layer, d.hidden, d.inter = cfg.num_hidden_layers, cfg.hidden_size, cfg.intermediate_size
+        d.n_q_head, d.n_kv_head, d.head_dim, d.vocab, d.n_stream = cfg.num_attention_heads, cfg.num_key_value_heads, cfg.head_dim, cfg.vocab_size, 1
+        d.layer_ptrs, d.lm_head = self._stack_layer_ptrs().data_ptr(), self.w.lm_head.data_ptr()
+        check(self.lib.svln_decode_stack_pack(C.byref(d), buf.data_ptr(), buf.numel(), cur_stream()))
 
     def _stack_desc(self, state: "_DecodeState", tok: torch.Tensor):
         """svln_decode_stack descriptor bound to this state's device tensors (built once per state)."""

@@ -218,6 +218,7 @@ def test_bf16_tie_goes_to_the_lowest_index_on_every_decode_path(big, cuda):
             w2 = lm32.lm_head(x)
         assert float(w2[hi]) > float(w2[lo]) and abs(float(w2[hi] - w2[lo])) < 2.0 ** -12 * abs(top), "nudge is not a near-tie"
         assert float(w2[hi].bfloat16()) == float(w2[lo].bfloat16()) == float(w2.bfloat16().max())
+        eng.repack_decode_weights()          # the fused step reads the packed copy of lm_head
         picks = {}
         for name, n, stack in (("stack", 1, True), ("gemv", 1, False), ("gemv2", 2, False), ("cublas", 5, False)):
             eng.use_stack = stack
@@ -235,6 +236,7 @@ def test_bf16_tie_goes_to_the_lowest_index_on_every_decode_path(big, cuda):
         if saved is not None:
             lm_head[saved[0]] = saved[1]
             lm32.lm_head.weight.data[saved[0]] = saved[2]
+            eng.repack_decode_weights()
 
 
 def _alone(eng, emb, env, n_new, eos=None):
