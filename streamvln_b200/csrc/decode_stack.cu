@@ -854,8 +854,12 @@ __device__ __forceinline__ void run_gemv(const StackParams& p, unsigned char* sm
     else gemv_phase<NB, RPU>(p, smem, W, K, n_units, rowfn, mid, epi, pol, tr_li, tr_ph);
 }
 
+// FEED = 1 launches three warpgroups: two of compute warps and one that holds the producer thread.  The kernel is
+// compiled for 168 registers (384 threads); the producer's warpgroup hands its registers back (setmaxnreg.dec) and the
+// compute warpgroups grow to 232 (setmaxnreg.inc), which takes most spills out of the main loops and the attention item.
+constexpr int TK_EXTRA_THREADS = 128;
 template <int NB, int FEED>
-__global__ void __launch_bounds__(MK_THREADS + FEED * 32, 1)
+__global__ void __launch_bounds__(MK_THREADS + FEED * TK_EXTRA_THREADS, 1)
 decode_stack_kernel(const __grid_constant__ StackParams p) {
     extern __shared__ __align__(1024) unsigned char smem[];
     const int tid = threadIdx.x, warp = tid >> 5;
@@ -883,11 +887,13 @@ decode_stack_kernel(const __grid_constant__ StackParams p) {
             for (int s = 0; s < TK_SLOTS; ++s) { tk_mbar_init(feed.full + s * 8, 1); tk_mbar_init(feed.empty + s * 8, MK_WARPS); }
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
-        __syncthreads();                                 // all nine warps, once
-        if (warp == MK_WARPS) {
-            if ((tid & 31) == 0) tk_producer(p, feed, pol);
+        __syncthreads();                                 // all twelve warps, once
+        if (warp >= MK_WARPS) {
+            asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
+            if (tid == MK_THREADS) tk_producer(p, feed, pol);
             return;
         }
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 240;");
     }
 
     // this CTA's share of each phase (balanced contiguous ranges)
@@ -1410,7 +1416,7 @@ int svln_decode_stack_step(const svln_kv_arena* arena, const svln_decode_stack* 
     SVLN_CUDA(cudaMemsetAsync(p.sync, 0, 64 * 4, st));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(G);
-    cfg.blockDim = dim3(MK_THREADS + (packed_feed ? 32 : 0));
+    cfg.blockDim = dim3(MK_THREADS + (packed_feed ? TK_EXTRA_THREADS : 0));
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
