@@ -325,7 +325,9 @@ size_t svln_decode_stack_workspace_bytes(const svln_decode_stack* desc);
  * layer linears and lm_head (same bytes, `svln_decode_stack_packed_bytes` of them: 15.3 GB for Qwen2-7B) laid out as one
  * contiguous stream per CTA in consumption order, which a single producer thread per SM feeds to shared memory with
  * bulk copies (cp.async.bulk + mbarriers) across phase boundaries.  The layout depends on the SM count of the current
- * device; pack on the device that runs the step.  `packed` 128-byte aligned.  Reads layer_ptrs (synchronises `stream`). */
+ * device; pack on the device that runs the step (the library remembers what each packed buffer of the process was packed
+ * for; a step on a buffer it does not know, or packed for other dims / another grid, returns SVLN_ERR_INVALID).
+ * `packed` 128-byte aligned.  Reads layer_ptrs (synchronises `stream`). */
 size_t svln_decode_stack_packed_bytes(const svln_decode_stack* desc);
 int svln_decode_stack_pack(const svln_decode_stack* desc, void* packed, size_t packed_bytes, svln_stream_t stream);
 /* SVLN_ERR_RANGE when n_stream > 1 (the caller falls back to the launch-per-op path; larger batches are GEMMs). */

@@ -1301,6 +1301,25 @@ static TkDims tk_dims(const svln_decode_stack* d, int G) {
     return TkDims{d->n_layer, d->hidden, d->inter, d->n_q_head, d->n_kv_head, d->vocab, G};
 }
 
+// The packed layout depends on the grid and on the model dims: remember what every packed buffer of this process was
+// packed for, so that a step on a stale or foreign buffer fails loudly instead of streaming the wrong bytes.
+struct PackedRecord { const void* ptr; TkDims dims; };
+static PackedRecord g_packed[32];
+static int g_packed_n = 0;
+static bool same_dims(const TkDims& a, const TkDims& b) {
+    return a.n_layer == b.n_layer && a.D == b.D && a.I == b.I && a.Hq == b.Hq && a.Hkv == b.Hkv && a.V == b.V && a.G == b.G;
+}
+static void packed_remember(const void* ptr, const TkDims& dims) {
+    for (int i = 0; i < g_packed_n; ++i)
+        if (g_packed[i].ptr == ptr) { g_packed[i].dims = dims; return; }
+    g_packed[g_packed_n < 32 ? g_packed_n++ : 31] = PackedRecord{ptr, dims};
+}
+static bool packed_matches(const void* ptr, const TkDims& dims) {
+    for (int i = 0; i < g_packed_n; ++i)
+        if (g_packed[i].ptr == ptr) return same_dims(g_packed[i].dims, dims);
+    return false;
+}
+
 size_t svln_decode_stack_packed_bytes(const svln_decode_stack* d) {
     if (!d || d->n_layer < 1 || d->hidden < 32 || d->inter < 32 || d->n_q_head < 1 || d->n_kv_head < 1 || d->vocab < 1 ||
         d->head_dim != HD) return 0;
@@ -1338,6 +1357,7 @@ int svln_decode_stack_pack(const svln_decode_stack* d, void* packed, size_t pack
         pack((const void*)L[4], 3, li);
     }
     pack(d->lm_head, 4, 0);
+    packed_remember(packed, dims);
     return check_launch("tk_pack_kernel");
 }
 
@@ -1389,6 +1409,8 @@ int svln_decode_stack_step(const svln_kv_arena* arena, const svln_decode_stack* 
         // may fill it whatever the compute warps are doing
         SVLN_REQUIRE(d->packed_bytes >= svln_decode_stack_packed_bytes(d), SVLN_ERR_NOMEM,
                      "svln_decode_stack_step: packed stream %zu < %zu bytes", d->packed_bytes, svln_decode_stack_packed_bytes(d));
+        SVLN_REQUIRE(packed_matches(d->packed, tk_dims(d, G)), SVLN_ERR_INVALID,
+                     "svln_decode_stack_step: `packed` was not written by svln_decode_stack_pack for these dims and a grid of %d CTAs", G);
         size_t ring = align_up((size_t)p.off_part + (size_t)MK_WARPS * TK_WIDE_ROWS * B * 4, 1024);
         if (ring < (size_t)TK_ATTN_SMEM) ring = TK_ATTN_SMEM;
         p.off_ring = (int)ring;
