@@ -38,6 +38,15 @@
 // round 2: cp.async.bulk.prefetch.L2 of the bytes right behind the ring at every phase start (64 / 160 / 320 KB per CTA:
 // 4 / 6 / 9 % slower) and of the CTA's O slice + 0 / 256 / 512 KB of its gate/up slice from the idle warps during the
 // attention phase (1.5 / 3 / 8 % slower) - profiles/r2_decode_stack_experiments.md.
+// Round 2, the default feed (FEED = 1, descriptor field `packed`): the weights are re-laid by svln_decode_stack_pack as
+// one contiguous stream per CTA in consumption order and copied into a 3 x 32 KB shared-memory ring by ONE producer
+// thread per SM (cp.async.bulk + mbarriers) that runs ahead across phase boundaries; the kernel launches three
+// warpgroups, the producer's gives its registers back and the compute warps run with 240 (setmaxnreg); residual adds sit
+// in the O / down epilogues, x of those two projections arrives by a bulk copy, everything a phase needs that does
+// not depend on the step (norm weights, bias, RoPE factors) is fetched before its barrier is waited for; the grid
+// barrier is a release reduction + relaxed polls.  2.75 ms per token at 7B (0.79-0.80 of the measured HBM peak)
+// against 3.3-3.4 for the LDGSTS feed (FEED = 0, kept: descriptor without `packed`).  See the "packed weight stream"
+// block below and profiles/r2_decode_stack_experiments.md.
 // Rounding points are those of the unfused path (fused_ops.cu, kv_window.cu rope8, gemv.cu), i.e. HF's bf16
 // modules; accumulation order differs from cuBLAS, which the parity tolerance (1e-2 on logits) covers.
 #include <stdlib.h>
@@ -568,12 +577,12 @@ __device__ __noinline__ void attn_item(const DecodeParams& dp, int split, int kv
 
 // ---- packed weight stream (FEED = 1) ------------------------------------------------------------------------------
 // svln_decode_stack_pack re-lays the weights of the step once: every CTA's share of every linear, in the order the CTA
-// consumes it, as ONE contiguous byte stream per CTA (layer by layer: QKV, O, gate/up, down; then lm_head).  A ninth
-// warp (one thread) walks that stream with 1-D bulk copies (cp.async.bulk, L2 evict-first) into a ring of TK_SLOTS x
-// 16 KB stages guarded by full/empty mbarriers.  It knows nothing of phases or grid barriers, so it keeps streaming
+// consumes it, as ONE contiguous byte stream per CTA (layer by layer: QKV, O, gate/up, down; then lm_head).  One
+// thread of a third warpgroup walks that stream with 1-D bulk copies (cp.async.bulk, L2 evict-first) into a ring of
+// TK_SLOTS x 32 KB stages guarded by full/empty mbarriers.  It knows nothing of phases or grid barriers, so it keeps streaming
 // while the compute warps sit in an epilogue, a grid barrier, a preamble or the attention phase: every phase starts
-// on a full ring (112 KB per SM, 16.6 MB chip-wide; all of a CTA's O slice is resident before the attention phase
-// ends), and the 3-6 k cycles of LDGSTS issue per phase (profiles/r2_decode_stack_experiments.md) are gone.  Measured
+// on a full ring (96 KB per SM, 14 MB chip-wide: more than half of a CTA's O slice is resident before the attention
+// phase ends), and the 3-6 k cycles of LDGSTS issue per phase (profiles/r2_decode_stack_experiments.md) are gone.  Measured
 // first with scripts/tma_stream_probe.cu: one thread per SM sustains 6.1-6.3 TB/s with 16-32 KB copies (2-D tensor
 // boxes of fewer than ~128 rows do not: 100-200 ns per box).
 // Layout of one stage: [k32-step][row of the group][64 B]: lane (g, t) of the warp that owns a k32-step reads the
