@@ -534,7 +534,7 @@ __device__ __forceinline__ void preamble_copy(const StackParams& p, unsigned cha
 
 // merge the split partials of (stream b, kv head kvh): warp <-> query row, lane <-> 4 dims; same arithmetic and
 // split order as attn_decode_combine_kernel, with all loads of a row in flight together
-__device__ __noinline__ void combine_splits(const StackParams& p, int b, int kvh) {
+__device__ __forceinline__ void combine_splits(const StackParams& p, int b, int kvh) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = p.Hq / p.Hkv;
     const int64_t slot0 = ((int64_t)b * p.Hkv + kvh) * p.n_splits;
@@ -570,7 +570,7 @@ __device__ __noinline__ void combine_splits(const StackParams& p, int b, int kvh
 }
 
 template <int MODE, int STAGES = DSTAGES>
-__device__ __noinline__ void attn_item(const DecodeParams& dp, int split, int kvh, int b, unsigned char* smem, int tid) {
+__device__ __forceinline__ void attn_item(const DecodeParams& dp, int split, int kvh, int b, unsigned char* smem, int tid) {
     attn_decode_body<1, MODE, STAGES, STAGES != DSTAGES>(dp, split, kvh, b, smem, tid);
 }
 
@@ -679,7 +679,7 @@ __device__ __forceinline__ void tk_mbar_wait(uint32_t bar, uint32_t parity, unsi
 }
 
 // the producer thread: walks the CTA's packed stream stage by stage, in the order gemv_phase_tk consumes it
-__device__ __noinline__ void tk_producer(const StackParams& p, TkFeed f, uint64_t pol) {
+__device__ __forceinline__ void tk_producer(const StackParams& p, TkFeed f, uint64_t pol) {
     const TkDims d = {p.n_layer, p.D, p.I, p.Hq, p.Hkv, p.V, p.G};
     const int c = blockIdx.x;
     const unsigned char* src = p.packed + tk_cta_base(d, c);
