@@ -594,7 +594,7 @@ __device__ __forceinline__ void attn_item(const DecodeParams& dp, int split, int
 #define TK_XCOPY 3            // bit 0: x of the O projection by bulk copy, bit 1: x of the down projection
 #endif
 constexpr int TK_SLOT_BYTES = 32768;
-constexpr int TK_SLOTS = 3;
+constexpr int TK_SLOTS = 4;
 constexpr int TK_ATTN_STAGES = 2;                  // K/V tile stages of the in-kernel attention item: 64 KB
 constexpr int TK_ATTN_SMEM = TK_ATTN_STAGES * 2 * TILE_BYTES;
 constexpr int TK_WIDE_ROWS = 256;
