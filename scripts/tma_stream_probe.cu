@@ -330,11 +330,9 @@ int main() {
         printf("%-50s %7.1f us  %6.0f GB/s\n", c.name, best * 1e3, mbytes * c.passes / best / 1e6); fflush(stdout);
     }
     long long* cyc; CK(cudaMalloc(&cyc, 8));
-    // L2-resident source (256 KB per CTA, 64 passes): the handshake's own ceiling, cycles per stage
-    for (int stage : {8192, 16384, 32768}) {
-        const size_t small = (size_t)148 * 262144;
-        run_feed<4, 1>(W, small, stage, 64, sink, cyc, flush, e0, e1);
-        run_feed<6, 1>(W, small, stage, 64, sink, cyc, flush, e0, e1);
+    // source alignment: stages of 24960 / 32000 B keep every second copy 64-byte (not 128-byte) aligned
+    for (int stage : {24576, 24960, 25088, 32000, 32768}) {
+        run_feed<4, 1>(W, bytes, stage, 4, sink, cyc, flush, e0, e1);
     }
     return 0;
 }
