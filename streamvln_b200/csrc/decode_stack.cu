@@ -39,12 +39,13 @@
 // 4 / 6 / 9 % slower) and of the CTA's O slice + 0 / 256 / 512 KB of its gate/up slice from the idle warps during the
 // attention phase (1.5 / 3 / 8 % slower) - profiles/r2_decode_stack_experiments.md.
 // Round 2, the default feed (FEED = 1, descriptor field `packed`): the weights are re-laid by svln_decode_stack_pack as
-// one contiguous stream per CTA in consumption order and copied into a 3 x 32 KB shared-memory ring by ONE producer
+// one contiguous stream per CTA in consumption order and copied into a 4 x 32 KB shared-memory ring by ONE producer
 // thread per SM (cp.async.bulk + mbarriers) that runs ahead across phase boundaries; the kernel launches three
 // warpgroups, the producer's gives its registers back and the compute warps run with 240 (setmaxnreg); residual adds sit
 // in the O / down epilogues, x of those two projections arrives by a bulk copy, everything a phase needs that does
 // not depend on the step (norm weights, bias, RoPE factors) is fetched before its barrier is waited for; the grid
-// barrier is a release reduction + relaxed polls.  2.75 ms per token at 7B (0.79-0.80 of the measured HBM peak)
+// barrier is a release reduction + relaxed polls; nothing is called (calls cost caller-saved spills): no stack frame.
+// 2.64 ms per token at 7B (0.82-0.83 of the measured HBM peak)
 // against 3.3-3.4 for the LDGSTS feed (FEED = 0, kept: descriptor without `packed`).  See the "packed weight stream"
 // block below and profiles/r2_decode_stack_experiments.md.
 // Rounding points are those of the unfused path (fused_ops.cu, kv_window.cu rope8, gemv.cu), i.e. HF's bf16
@@ -581,7 +582,7 @@ __device__ __forceinline__ void attn_item(const DecodeParams& dp, int split, int
 // thread of a third warpgroup walks that stream with 1-D bulk copies (cp.async.bulk, L2 evict-first) into a ring of
 // TK_SLOTS x 32 KB stages guarded by full/empty mbarriers.  It knows nothing of phases or grid barriers, so it keeps streaming
 // while the compute warps sit in an epilogue, a grid barrier, a preamble or the attention phase: every phase starts
-// on a full ring (96 KB per SM, 14 MB chip-wide: more than half of a CTA's O slice is resident before the attention
+// on a full ring (128 KB per SM, 19 MB chip-wide: three quarters of a CTA's O slice are resident before the attention
 // phase ends), and the 3-6 k cycles of LDGSTS issue per phase (profiles/r2_decode_stack_experiments.md) are gone.  Measured
 // first with scripts/tma_stream_probe.cu: one thread per SM sustains 6.1-6.3 TB/s with 16-32 KB copies (2-D tensor
 // boxes of fewer than ~128 rows do not: 100-200 ns per box).
