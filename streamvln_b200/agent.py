@@ -98,6 +98,13 @@ class VLNEvaluator:
         memory_token_index = tokenizer.convert_tokens_to_ids("<memory>")
         tokenizer.chat_template = ("{% for message in messages %}{{'<|im_start|>' + message['role'] + '\n' + message['content'] "
                                    "+ '<|im_end|>' + '\n'}}{% endfor %}{% if add_generation_prompt %}{{ '<|im_start|>assistant\n' }}{% endif %}")
+        # the steady-turn prompt is the same text every turn: tokenise a given conversation once (0.2 ms of host time per
+        # turn sits between the previous turn's ids and this turn's first launch); the in-place edit of the caller's
+        # messages is kept
+        memo = self.__dict__.setdefault("_prompt_memo", {})
+        key = (id(tokenizer), add_system, system_message,
+               tuple(tuple((m.get("from", m.get("role")), m.get("value", m.get("content"))) for m in src) for src in sources))
+        hit = memo.get(key)
         conversations, input_ids = [], []
         for source in sources:
             prompt = self.conjunctions[0] + DEFAULT_IMAGE_TOKEN
@@ -105,6 +112,8 @@ class VLNEvaluator:
                 source[0]["value"] += f" {prompt}."
             else:
                 source[0]["value"] = f"{prompt}."
+            if hit is not None:
+                continue
             if roles[source[0]["from"]] != roles["human"]:
                 source = source[1:]
             input_id: List[int] = []
@@ -118,7 +127,12 @@ class VLNEvaluator:
             input_id = [IMAGE_TOKEN_INDEX if t == image_token_index else MEMORY_TOKEN_INDEX if t == memory_token_index else t
                         for t in input_id]
             input_ids.append(input_id)
-        return torch.tensor(input_ids, dtype=torch.long), conversations
+        if hit is not None:
+            return hit[0].clone(), list(hit[1])
+        out = torch.tensor(input_ids, dtype=torch.long)
+        if len(memo) < 256:
+            memo[key] = (out.clone(), list(conversations))
+        return out, conversations
 
     # ------------------------------------------------------------------------------------------
     def prepare(self, idx, rgb, instruction_text: str = "", run_model: bool = False, depth=None, pose=None, intrinsic=None,
