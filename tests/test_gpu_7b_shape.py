@@ -343,19 +343,14 @@ def test_zz_print_logit_error_stats():
         print(f"  {what:32s} {p_all:.2e} {p_big:.2e} | {h_all:.2e} {h_big:.2e} | {ph_all:.2e}")
 
 
-def test_decode_stack_feeds_agree(svln_lib, cuda):
-    """The two weight feeds of svln_decode_stack_step - the packed stream (bulk copies by a producer thread; default) and
-    the row-major LDGSTS feed (descriptor without `packed`) - are the same arithmetic up to the summation order of the wide
-    phases: logits of three decode steps agree to 1e-2 (each is within the HF tolerance on its own) and pick the same ids.
-    7B widths, 2 layers, contexts 3 / 64 / 700."""
+def _feeds_agree(cfg, ctxs, cuda):
     import os
-    from streamvln_b200.qwen2 import Chunk, Qwen2Config, Qwen2Engine, Qwen2Weights
+    from streamvln_b200.qwen2 import Chunk, Qwen2Engine, Qwen2Weights
 
-    cfg = Qwen2Config(num_hidden_layers=2)
     w = Qwen2Weights.random(cfg, cuda, seed=0)
     old = os.environ.get("SVLN_STACK_FEED")
     try:
-        for n_ctx in (3, 64, 700):
+        for n_ctx in ctxs:
             outs = []
             for feed in ("1", "0"):
                 os.environ["SVLN_STACK_FEED"] = feed
@@ -373,10 +368,32 @@ def test_decode_stack_feeds_agree(svln_lib, cuda):
                 del eng
             a, b = outs
             rel = float((a - b).norm() / b.norm())
-            assert rel <= 1e-2, (n_ctx, rel)
-            assert bool((a.argmax(-1) == b.argmax(-1)).all()), n_ctx
+            assert rel <= 1e-2, (cfg.hidden_size, n_ctx, rel)
+            assert bool((a.argmax(-1) == b.argmax(-1)).all()), (cfg.hidden_size, n_ctx)
     finally:
         if old is None:
             os.environ.pop("SVLN_STACK_FEED", None)
         else:
             os.environ["SVLN_STACK_FEED"] = old
+        del w
+        torch.cuda.empty_cache()
+
+
+def test_decode_stack_feeds_agree(svln_lib, cuda):
+    """The two weight feeds of svln_decode_stack_step - the packed stream (bulk copies by a producer thread; default) and
+    the row-major LDGSTS feed (descriptor without `packed`) - are the same arithmetic up to the summation order of the wide
+    phases: logits of three decode steps agree to 1e-2 (each is within the HF tolerance on its own) and pick the same ids.
+    7B widths, 2 layers, contexts 3 / 64 / 700."""
+    from streamvln_b200.qwen2 import Qwen2Config
+
+    _feeds_agree(Qwen2Config(num_hidden_layers=2), (3, 64, 700), cuda)
+
+
+def test_decode_stack_feeds_agree_other_widths(svln_lib, cuda):
+    """The packed layout is generic in the model dims: widths that give a CTA more than 32 QKV rows (two row groups in
+    the narrow phases), 8 kv heads (4 query heads per group), an inter size and a vocabulary that do not divide by the grid
+    (hidden 4096, 32:8 heads, inter 14336, vocab 128256; 2 layers)."""
+    from streamvln_b200.qwen2 import Qwen2Config
+
+    _feeds_agree(Qwen2Config(num_hidden_layers=2, hidden_size=4096, intermediate_size=14336, num_attention_heads=32,
+                             num_key_value_heads=8, vocab_size=128256), (65, 1500), cuda)
