@@ -287,7 +287,8 @@ int svln_pool_bilinear(const void* feat, int n_frames, int grid_in, int grid_out
                        svln_stream_t stream);
 
 /* ----------------------------------------------------------------------------------------
- * Fused decode stack: one persistent launch = one greedy decode step of ONE stream (n_stream = 1)
+ * Fused decode stack: one persistent launch = one greedy decode step of ONE or TWO streams (n_stream = 1, 2;
+ * two streams share one pass over the weights and need the packed weight stream)
  * (embedding row -> n_layer x [RMSNorm, QKV + bias + RoPE + append to the arena, split-KV attention, O,
  *  RMSNorm, SwiGLU MLP] -> final norm -> lm_head -> argmax).  Replaces the per-token forward of HF's greedy
  * loop (transformers 4.45.1 GenerationMixin._sample -> Qwen2ForCausalLM.forward; reached from
@@ -301,7 +302,7 @@ int svln_pool_bilinear(const void* feat, int n_frames, int grid_in, int grid_out
  * ---------------------------------------------------------------------------------------- */
 typedef struct svln_decode_stack {
     int32_t n_layer, hidden, inter, n_q_head, n_kv_head, head_dim, vocab;
-    int32_t n_stream;            /* 1 (arrays below keep the [n_stream] shape for a later multi-stream variant) */
+    int32_t n_stream;            /* 1 or 2 (2 only with `packed`) */
     float rms_eps, attn_scale;
     const void* layer_ptrs;
     const void* embed;           /* [vocab, hidden] bf16 */
@@ -330,7 +331,8 @@ size_t svln_decode_stack_workspace_bytes(const svln_decode_stack* desc);
  * `packed` 128-byte aligned.  Reads layer_ptrs (synchronises `stream`). */
 size_t svln_decode_stack_packed_bytes(const svln_decode_stack* desc);
 int svln_decode_stack_pack(const svln_decode_stack* desc, void* packed, size_t packed_bytes, svln_stream_t stream);
-/* SVLN_ERR_RANGE when n_stream > 1 (the caller falls back to the launch-per-op path; larger batches are GEMMs). */
+/* SVLN_ERR_RANGE when n_stream > 2, or 2 without `packed` (the caller falls back to the launch-per-op path; larger
+ * batches are GEMMs). */
 int svln_decode_stack_step(const svln_kv_arena* arena, const svln_decode_stack* desc, svln_stream_t stream);
 /* A grid barrier that times out (a bug, or a grid that could not be made co-resident) does not hang the GPU: the
  * kernel finishes and reports token -1 for every stream.  This call (synchronous) returns 0 when the last launch on

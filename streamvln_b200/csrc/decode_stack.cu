@@ -65,7 +65,7 @@ constexpr int MK_CAP = 304;          // rows per group (multiple of 16; gate/up 
 // for some of the weight copies, an LDGSTS form ([R+UR0], desc[UR1]) that does not reference the cache-policy
 // descriptor registers it has just loaded and raises "Warp Illegal Instruction" on the B200 (pinned down with
 // cuda-gdb; laundering the address, a 64-bit shared operand and creating the policy locally did not avoid it).
-constexpr int MK_MAX_B = 1;
+constexpr int MK_MAX_B = 2;          // 2 streams only with the packed feed (the LDGSTS feed's two-stream build hits the ptxas fault below)
 constexpr int MK_MAX_SPLITS = 32;
 constexpr int MK_XPAD = 32;          // elements between the x rows of two streams: 64 B, spreads the banks
 constexpr int MK_MISC = 4096;        // bytes of misc shared memory (reductions, flags, combine weights)
@@ -1456,16 +1456,20 @@ int svln_decode_stack_step(const svln_kv_arena* arena, const svln_decode_stack* 
     attr[0].val.cooperative = 1;
     cfg.attrs = attr;
     cfg.numAttrs = coop ? 1 : 0;
-    static size_t smem_set[2][64] = {{0}};  // per device: function attributes do not carry over to another GPU
+    static size_t smem_set[3][64] = {{0}};  // per device: function attributes do not carry over to another GPU
     int dev_i = 0;
     SVLN_CUDA(cudaGetDevice(&dev_i));
     dev_i = dev_i < 0 || dev_i >= 64 ? 0 : dev_i;
-    if (smem > smem_set[packed_feed][dev_i]) {
-        if (packed_feed) SVLN_CUDA(cudaFuncSetAttribute(decode_stack_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SVLN_REQUIRE(B == 1 || packed_feed, SVLN_ERR_RANGE, "svln_decode_stack_step: n_stream %d needs the packed weight stream", B);
+    const int variant = packed_feed ? B : 0;               // 0: <1, 0>, 1: <1, 1>, 2: <2, 1>
+    if (smem > smem_set[variant][dev_i]) {
+        if (variant == 2) SVLN_CUDA(cudaFuncSetAttribute(decode_stack_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        else if (variant == 1) SVLN_CUDA(cudaFuncSetAttribute(decode_stack_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         else SVLN_CUDA(cudaFuncSetAttribute(decode_stack_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        smem_set[packed_feed][dev_i] = smem;
+        smem_set[variant][dev_i] = smem;
     }
-    if (packed_feed) SVLN_CUDA(cudaLaunchKernelEx(&cfg, decode_stack_kernel<1, 1>, p));
+    if (variant == 2) SVLN_CUDA(cudaLaunchKernelEx(&cfg, decode_stack_kernel<2, 1>, p));
+    else if (variant == 1) SVLN_CUDA(cudaLaunchKernelEx(&cfg, decode_stack_kernel<1, 1>, p));
     else SVLN_CUDA(cudaLaunchKernelEx(&cfg, decode_stack_kernel<1, 0>, p));
     return check_launch("decode_stack_kernel");
 }

@@ -384,7 +384,7 @@ class Qwen2Engine:
     def _decode_runner(self, envs: Sequence[int], use_graph: bool) -> "_DecodeRunner":
         return _DecodeRunner(self, list(envs), use_graph)
 
-    STACK_MAX_STREAMS = 1
+    STACK_MAX_STREAMS = 2          # two streams only with the packed weight feed (svln_decode_stack_step)
 
     def _stack_layer_ptrs(self) -> torch.Tensor:
         if self._layer_ptrs is None:
@@ -471,7 +471,7 @@ class Qwen2Engine:
         this sequence of launches is CUDA-graph capturable."""
         cfg = self.cfg
         state.kv_len.add_(1)
-        if self.use_stack and tok.numel() <= self.STACK_MAX_STREAMS:
+        if self.use_stack and tok.numel() <= (self.STACK_MAX_STREAMS if os.environ.get("SVLN_STACK_FEED", "1") != "0" else 1):
             d = self._stack_desc(state, tok)
             state.stack_tok_in.copy_(tok)
             timed = self.prof is not None and not torch.cuda.is_current_stream_capturing()

@@ -174,6 +174,53 @@ def test_decode_stack_step_at_7b_dims(big, cuda, kv_len):
         eng._graphs.clear()
 
 
+@pytest.mark.parametrize("kv_lens", [(65, 3000), (1000, 1000), (1, 4090)])
+def test_decode_stack_two_streams_at_7b_dims(big, cuda, kv_lens):
+    """n_stream = 2 through svln_decode_stack_step (packed weight feed): two streams with different cache lengths share
+    one weight pass; each stream's logits vs its own fp32 / bf16 HF run, step by step."""
+    from transformers import DynamicCache
+    from streamvln_b200.qwen2 import Chunk
+
+    eng, lm32, lm16 = big
+    assert eng.use_stack and eng.STACK_MAX_STREAMS >= 2
+    n_steps = 3
+    eng.keep_decode_logits = True
+    eng._graphs.clear()
+    try:
+        toks, caches = [], []
+        for b, n_ctx in enumerate(kv_lens):
+            env = 2 + b
+            emb = _emb(n_ctx, eng.cfg.hidden_size, 300 + n_ctx + b, cuda)
+            eng.arena.reset_env(env)
+            toks.append(eng.forward(emb.clone(), [Chunk(env, 0, n_ctx, n_ctx)]).argmax(-1).reshape(1))
+            c32, c16 = DynamicCache(config=lm32.config), DynamicCache(config=lm16.config)
+            with torch.no_grad():
+                lm32(inputs_embeds=emb[None].float(), past_key_values=c32, use_cache=True)
+                lm16(inputs_embeds=emb[None], past_key_values=c16, use_cache=True)
+            caches.append((c32, c16))
+        tok = torch.cat(toks)
+        runner = eng._decode_runner([2, 3], True)
+        for step in range(n_steps):
+            fed = tok.clone()
+            tok = runner.step(tok)
+            assert runner.graph.state.stack is not None, "two streams must take the fused stack"
+            assert int(tok.min()) >= 0, "a grid barrier of the fused stack timed out"
+            for b, (c32, c16) in enumerate(caches):
+                with torch.no_grad():
+                    want = lm32(input_ids=fed[b].reshape(1, 1), past_key_values=c32, use_cache=True).logits[0, -1]
+                    want16 = lm16(input_ids=fed[b].reshape(1, 1), past_key_values=c16, use_cache=True).logits[0, -1].float()
+                got = runner.graph.state.stack_logits[b]
+                _check_logits(got, want, want16, f"decode stack x2, stream {b}, kv {kv_lens[b] + step + 1}")
+                assert torch.equal(got, got.bfloat16().float())
+                assert int(tok[b]) == int(got.argmax())
+                assert _greedy_ok(int(tok[b]), want16), (b, int(tok[b]), int(want16.argmax()))
+        runner.finish()
+        assert [eng.arena.lens[2], eng.arena.lens[3]] == [n + n_steps for n in kv_lens]
+    finally:
+        eng.keep_decode_logits = False
+        eng._graphs.clear()
+
+
 def test_bf16_tie_goes_to_the_lowest_index_on_every_decode_path(big, cuda):
     """Two lm_head rows whose fp32 logits differ by far less than a bf16 ulp: HF (bf16 lm_head, .float(), argmax) sees
     a tie and takes the LOWER index although the higher row's unrounded sum is larger.  The fused stack (1 stream),
@@ -220,7 +267,7 @@ def test_bf16_tie_goes_to_the_lowest_index_on_every_decode_path(big, cuda):
         assert float(w2[hi].bfloat16()) == float(w2[lo].bfloat16()) == float(w2.bfloat16().max())
         eng.repack_decode_weights()          # the fused step reads the packed copy of lm_head
         picks = {}
-        for name, n, stack in (("stack", 1, True), ("gemv", 1, False), ("gemv2", 2, False), ("cublas", 5, False)):
+        for name, n, stack in (("stack", 1, True), ("stack2", 2, True), ("gemv", 1, False), ("gemv2", 2, False), ("cublas", 5, False)):
             eng.use_stack = stack
             eng._graphs.clear()
             for env in range(n_env):

@@ -165,7 +165,9 @@ def test_decode_stack_abi_argument_checks():
     d.n_layer, d.hidden, d.inter, d.n_q_head, d.n_kv_head, d.head_dim, d.vocab, d.n_stream = 28, 3584, 18944, 28, 4, 128, 152064, 1
     assert lib.svln_decode_stack_workspace_bytes(C.byref(d)) > 14 * 3584          # room for the activation vectors
     d.n_stream = 2
-    assert lib.svln_decode_stack_workspace_bytes(C.byref(d)) == 0                 # single-stream ABI
+    assert lib.svln_decode_stack_workspace_bytes(C.byref(d)) > 2 * 14 * 3584      # two streams: packed feed only
+    d.n_stream = 3
+    assert lib.svln_decode_stack_workspace_bytes(C.byref(d)) == 0                 # at most two
     d.n_stream = 1
     arena = _lib.KvArenaStruct()
     assert lib.svln_decode_stack_step(C.byref(arena), C.byref(d), None) == -22    # null arena base
