@@ -84,6 +84,11 @@ class VLNEvaluator:
         env = getattr(self, "_env", 0)
         self.model.reset_episode(env) if hasattr(self.model, "reset_episode") else self.model.reset_for_env(env)
 
+    def _conjunction(self) -> str:
+        """The phrase in front of the turn's <image> token.  The real-world agent fixes it (benchmark config: conjunctions[0]);
+        the Habitat evaluator draws it with random.choice (streamvln_eval.py:424) and overrides this."""
+        return self.conjunctions[0]
+
     def parse_actions(self, output: str) -> List[int]:
         """streamvln_agent.py:101-107"""
         matches = self._regex.findall(output)
@@ -102,12 +107,13 @@ class VLNEvaluator:
         # turn sits between the previous turn's ids and this turn's first launch); the in-place edit of the caller's
         # messages is kept
         memo = self.__dict__.setdefault("_prompt_memo", {})
-        key = (id(tokenizer), add_system, system_message,
+        picks = [self._conjunction() for _ in sources]
+        key = (id(tokenizer), add_system, system_message, tuple(picks),
                tuple(tuple((m.get("from", m.get("role")), m.get("value", m.get("content"))) for m in src) for src in sources))
         hit = memo.get(key)
         conversations, input_ids = [], []
-        for source in sources:
-            prompt = self.conjunctions[0] + DEFAULT_IMAGE_TOKEN
+        for source, pick in zip(sources, picks):
+            prompt = pick + DEFAULT_IMAGE_TOKEN
             if len(source[0]["value"]) != 0:
                 source[0]["value"] += f" {prompt}."
             else:

@@ -1,0 +1,46 @@
+"""The Habitat evaluation driver (`streamvln_b200.habitat_eval`) on the GPU with a real (tiny) StreamVLN: the loop with the
+CUDA image / depth processors and pinned H2D must walk the fake simulator exactly like the same loop with the host (PIL /
+numpy) processors - the kernels are bit-exact with the host paths, so the action logs are identical - and the slowfast
+mode must run the same driver."""
+import json
+import random
+import sys
+from pathlib import Path
+from types import SimpleNamespace
+
+import pytest
+
+sys.path.insert(0, str(Path(__file__).resolve().parent))
+import fake_env  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+def _walk(cuda, out_dir, gpu_preprocess, mode="reference"):
+    from streamvln_b200.habitat_eval import evaluate
+    from streamvln_b200.model import StreamVLNConfig, StreamVLNForCausalLM
+    from streamvln_b200.tokenizer import StubQwenTokenizer
+
+    cfg = StreamVLNConfig.tiny(vocab_size=512, layers=2, mode=mode)
+    m = StreamVLNForCausalLM(cfg, n_env=1, device=cuda, seed=3, lm_head_std=0.3)
+    args = SimpleNamespace(num_frames=32, num_future_steps=4, num_history=8, max_new_tokens=4, save_video=False,
+                           gpu_preprocess=gpu_preprocess, output_path=str(out_dir))
+    envs = []
+    random.seed(0)
+    res = evaluate(m, StubQwenTokenizer(512), args, env_factory=lambda: envs.append(fake_env.FakeEnv()) or envs[-1],
+                   sim_sensors=fake_env.fake_sensors(), filter_depth=lambda d, blur_type=None: d)
+    rows = [json.loads(l) for l in (Path(out_dir) / "result.json").read_text().splitlines()[:-1]]
+    return res, rows, envs[0].log
+
+
+def test_driver_gpu_processors_equal_host_processors(svln_lib, cuda, tmp_path):
+    a = _walk(cuda, tmp_path / "gpu", True)
+    b = _walk(cuda, tmp_path / "host", False)
+    assert a[2] == b[2] and a[1] == b[1] and a[0] == b[0]
+    assert a[0]["length"] == 7 and len(a[1]) == 7 and all(r["steps"] >= 1 for r in a[1])
+    assert max(r["steps"] for r in a[1]) > 32          # at least one episode crossed a window boundary on the real model
+
+
+def test_driver_runs_the_slowfast_mode(svln_lib, cuda, tmp_path):
+    res, rows, log = _walk(cuda, tmp_path / "sf", True, mode="slowfast")
+    assert res["length"] == 7 and len(log) == sum(r["steps"] for r in rows)
