@@ -16,6 +16,14 @@ import fake_env  # noqa: E402
 pytestmark = pytest.mark.gpu
 
 
+class NoStopEnv(fake_env.FakeEnv):
+    """A random-init model says STOP within a few turns; walking forward instead lets every episode run to its step cap
+    (up to 70 steps: two window boundaries)."""
+
+    def step(self, action):
+        return super().step(action if action != 0 else 1)
+
+
 def _walk(cuda, out_dir, gpu_preprocess, mode="reference"):
     from streamvln_b200.habitat_eval import evaluate
     from streamvln_b200.model import StreamVLNConfig, StreamVLNForCausalLM
@@ -27,7 +35,7 @@ def _walk(cuda, out_dir, gpu_preprocess, mode="reference"):
                            gpu_preprocess=gpu_preprocess, output_path=str(out_dir))
     envs = []
     random.seed(0)
-    res = evaluate(m, StubQwenTokenizer(512), args, env_factory=lambda: envs.append(fake_env.FakeEnv()) or envs[-1],
+    res = evaluate(m, StubQwenTokenizer(512), args, env_factory=lambda: envs.append(NoStopEnv()) or envs[-1],
                    sim_sensors=fake_env.fake_sensors(), filter_depth=lambda d, blur_type=None: d)
     rows = [json.loads(l) for l in (Path(out_dir) / "result.json").read_text().splitlines()[:-1]]
     return res, rows, envs[0].log
@@ -38,7 +46,7 @@ def test_driver_gpu_processors_equal_host_processors(svln_lib, cuda, tmp_path):
     b = _walk(cuda, tmp_path / "host", False)
     assert a[2] == b[2] and a[1] == b[1] and a[0] == b[0]
     assert a[0]["length"] == 7 and len(a[1]) == 7 and all(r["steps"] >= 1 for r in a[1])
-    assert max(r["steps"] for r in a[1]) > 32          # at least one episode crossed a window boundary on the real model
+    assert sorted(r["steps"] for r in a[1]) == [5, 9, 21, 33, 37, 64, 70]     # the step caps: two window boundaries crossed
 
 
 def test_driver_runs_the_slowfast_mode(svln_lib, cuda, tmp_path):
