@@ -15,11 +15,33 @@ __device__ __forceinline__ int32_t voxel_coord(float x, float voxel_size) {
     return (int32_t)q;
 }
 
+struct PruneSetup {               // optional by-products of the keys kernel (t_out == nullptr: keys only)
+    int32_t* t_out;
+    int64_t* seg_off;
+    int64_t* range_off;
+    unsigned* ticket;
+    int64_t n_segments, n_streams, stream_tokens, seg_tokens, n_tokens;
+    int pps, n_frames;
+};
+
 __global__ void __launch_bounds__(256)
 voxel_keys_kernel(const float* __restrict__ depth, const float* __restrict__ pose,
                   const float* __restrict__ intr, int H, int W, int G, float voxel_size,
-                  float max_depth, int64_t* __restrict__ key_out) {
+                  float max_depth, int64_t* __restrict__ key_out, PruneSetup su) {
     const int64_t f = blockIdx.x;
+    if (su.t_out) {
+        // the fused pipeline's bookkeeping rides along (it was three more launches): frame times, the (stream, period)
+        // dedup segment offsets, the per-stream range offsets and the compaction's arrival counter
+        const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;      // grid threads >= n_segments + 1
+        if (g <= su.n_segments) {
+            const int64_t s = g / su.pps, p = g % su.pps;
+            const int64_t o = s * su.stream_tokens + p * su.seg_tokens;
+            const int64_t lim = (s + 1) * su.stream_tokens;
+            su.seg_off[g] = o > lim ? lim : o;
+        }
+        if (g <= su.n_streams) su.range_off[g] = min(g * su.stream_tokens, su.n_tokens);
+        if (g == 0) *su.ticket = 0;
+    }
     const float* P = pose + f * 16;
     const float* K = intr + f * 16;
     const float fx = K[0], cx = K[2], fy = K[5], cy = K[6];
@@ -59,6 +81,7 @@ voxel_keys_kernel(const float* __restrict__ depth, const float* __restrict__ pos
             key = (vx << 42) | (vy << 21) | vz;
         }
         key_out[f * n_tok + tok] = key;
+        if (su.t_out) su.t_out[f * n_tok + tok] = (int32_t)(f % su.n_frames);
     }
 }
 
@@ -284,9 +307,56 @@ __device__ __forceinline__ uint32_t load_mask4(const uint8_t* __restrict__ mask,
     return bits;
 }
 
+// exclusive scan of block counts in place by one CTA of NT threads; blk_cnt[n_blocks] receives the total
+template <int NT>
+__device__ __forceinline__ void scan_block_counts(int32_t* blk_cnt, int64_t n_blocks, int32_t* __restrict__ n_keep_out) {
+    __shared__ int s_sw[32];
+    __shared__ int s_carry;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int NW = NT / 32;
+    for (int64_t b0 = 0; b0 < n_blocks; b0 += NT) {
+        const int64_t b = b0 + threadIdx.x;
+        const int v = b < n_blocks ? __ldcg(blk_cnt + b) : 0;
+        int inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int y = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += y;
+        }
+        if (lane == 31) s_sw[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            int w = lane < NW ? s_sw[lane] : 0;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int y = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= o) w += y;
+            }
+            s_sw[lane] = w;  // inclusive over warps
+        }
+        __syncthreads();
+        const int carry = s_carry;
+        const int excl = carry + (warp ? s_sw[warp - 1] : 0) + inc - v;
+        if (b < n_blocks) blk_cnt[b] = excl;
+        __syncthreads();
+        if (threadIdx.x == NT - 1) s_carry = carry + s_sw[NW - 1];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        blk_cnt[n_blocks] = s_carry;
+        if (n_keep_out) *n_keep_out = s_carry;
+    }
+}
+
+// per-block survivor counts; the LAST block to arrive (ticket counter, zeroed by the caller's previous launch) scans them,
+// so counting and scanning are one launch
 __global__ void __launch_bounds__(256)
-compact_count_kernel(const uint8_t* __restrict__ mask, int64_t n_tokens, int32_t* __restrict__ blk_cnt) {
+compact_count_scan_kernel(const uint8_t* __restrict__ mask, int64_t n_tokens, int32_t* __restrict__ blk_cnt,
+                          unsigned* __restrict__ ticket, int32_t* __restrict__ n_keep_out) {
     __shared__ int s_w[8];
+    __shared__ bool s_last;
     const int64_t base = (int64_t)blockIdx.x * CB + threadIdx.x * 4;
     int c = __popc(load_mask4(mask, base, n_tokens));
     c = (int)warp_sum((float)c);
@@ -296,56 +366,47 @@ compact_count_kernel(const uint8_t* __restrict__ mask, int64_t n_tokens, int32_t
         int tot = 0;
 #pragma unroll
         for (int w = 0; w < 8; ++w) tot += s_w[w];
-        blk_cnt[blockIdx.x] = tot;
+        __stcg(blk_cnt + blockIdx.x, tot);
+        __threadfence();
+        s_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
     }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    scan_block_counts<256>(blk_cnt, (int64_t)gridDim.x, n_keep_out);
+    if (threadIdx.x == 0) *ticket = 0;      // ready for the next call on this workspace
 }
 
-// exclusive scan of block counts in place; blk_cnt[n_blocks] receives the total (single CTA)
-__global__ void __launch_bounds__(1024)
-compact_scan_kernel(int32_t* __restrict__ blk_cnt, int64_t n_blocks, int32_t* __restrict__ n_keep_out) {
-    __shared__ int s_w[32];
-    __shared__ int s_carry;
-    if (threadIdx.x == 0) s_carry = 0;
-    __syncthreads();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int64_t b0 = 0; b0 < n_blocks; b0 += 1024) {
-        const int64_t b = b0 + threadIdx.x;
-        const int v = b < n_blocks ? blk_cnt[b] : 0;
-        int inc = v;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int y = __shfl_up_sync(0xffffffffu, inc, o);
-            if (lane >= o) inc += y;
-        }
-        if (lane == 31) s_w[warp] = inc;
-        __syncthreads();
-        if (warp == 0) {
-            int w = s_w[lane];
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int y = __shfl_up_sync(0xffffffffu, w, o);
-                if (lane >= o) w += y;
-            }
-            s_w[lane] = w;  // inclusive over warps
-        }
-        __syncthreads();
-        const int carry = s_carry;
-        const int excl = carry + (warp ? s_w[warp - 1] : 0) + inc - v;
-        if (b < n_blocks) blk_cnt[b] = excl;
-        __syncthreads();
-        if (threadIdx.x == 1023) s_carry = carry + s_w[31];
-        __syncthreads();
-    }
+// n_tokens == 0: nothing to count, the outputs are zeros
+__global__ void __launch_bounds__(32)
+compact_empty_kernel(int32_t* __restrict__ blk_cnt, int32_t* __restrict__ n_keep_out) {
     if (threadIdx.x == 0) {
-        blk_cnt[n_blocks] = s_carry;
-        if (n_keep_out) *n_keep_out = s_carry;
+        blk_cnt[0] = 0;
+        if (n_keep_out) *n_keep_out = 0;
     }
 }
 
 __global__ void __launch_bounds__(256)
 compact_write_kernel(const uint8_t* __restrict__ mask, int64_t n_tokens,
-                     const int32_t* __restrict__ blk_off, int32_t* __restrict__ idx_out) {
+                     const int32_t* __restrict__ blk_off, int32_t* __restrict__ idx_out, int n_write_blocks,
+                     const int64_t* __restrict__ range_off, int64_t n_offsets, int32_t* __restrict__ range_out) {
     __shared__ int s_w[8];
+    if ((int)blockIdx.x >= n_write_blocks) {
+        // trailing CTAs: survivors in front of each range boundary (per-stream keep offsets), one WARP per boundary (a
+        // thread per boundary walked up to 1023 mask bytes one dependent load at a time: 27 us for 65 boundaries)
+        const int64_t r = (int64_t)(blockIdx.x - n_write_blocks) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+        if (r >= n_offsets) return;
+        const int lane = threadIdx.x & 31;
+        int64_t off = range_off[r];
+        off = off < 0 ? 0 : (off > n_tokens ? n_tokens : off);
+        const int64_t b = off / CB;
+        int c = 0;
+        for (int64_t i = b * CB + lane; i < off; i += 32) c += mask[i] != 0;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+        if (lane == 0) range_out[r] = blk_off[b] + c;
+        return;
+    }
     const int64_t base = (int64_t)blockIdx.x * CB + threadIdx.x * 4;
     const uint32_t bits = load_mask4(mask, base, n_tokens);
     const int c = __popc(bits);
@@ -365,20 +426,6 @@ compact_write_kernel(const uint8_t* __restrict__ mask, int64_t n_tokens,
 #pragma unroll
     for (int q = 0; q < 4; ++q)
         if (bits & (1u << q)) idx_out[pos++] = (int32_t)(base + q);
-}
-
-__global__ void compact_ranges_kernel(const uint8_t* __restrict__ mask, int64_t n_tokens,
-                                      const int32_t* __restrict__ blk_off,
-                                      const int64_t* __restrict__ range_off, int64_t n_offsets,
-                                      int32_t* __restrict__ out) {
-    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= n_offsets) return;
-    int64_t off = range_off[r];
-    off = off < 0 ? 0 : (off > n_tokens ? n_tokens : off);
-    const int64_t b = off / CB;
-    int c = blk_off[b];
-    for (int64_t i = b * CB; i < off; ++i) c += mask[i] != 0;
-    out[r] = c;
 }
 
 // --------------------------------------------------------------------------- row gather
@@ -435,28 +482,6 @@ splice_rows_kernel(const int4* __restrict__ embed, const int4* __restrict__ feat
             }
         }
     }
-}
-
-// helper kernels for the fused pipeline: frame times and uniform offsets
-__global__ void fill_frame_t_kernel(int32_t* __restrict__ t, int64_t n_tokens, int tokens_per_frame,
-                                    int n_frames) {
-    const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (n < n_tokens) t[n] = (int32_t)((n / tokens_per_frame) % n_frames);
-}
-__global__ void fill_offsets_kernel(int64_t* __restrict__ off, int64_t count, int64_t step, int64_t total) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i <= count) off[i] = min(i * step, total);
-}
-
-// offsets of the (stream, period) dedup segments of S regular streams; entry n_segments = total
-__global__ void segment_offsets_kernel(int64_t* __restrict__ off, int64_t n_segments, int pps,
-                                       int64_t stream_tokens, int64_t seg_tokens) {
-    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g > n_segments) return;
-    const int64_t s = g / pps, p = g % pps;
-    const int64_t o = s * stream_tokens + p * seg_tokens;
-    const int64_t lim = (s + 1) * stream_tokens;
-    off[g] = o > lim ? lim : o;
 }
 
 // ------------------------------------------------------------------------------ host side
@@ -518,23 +543,25 @@ static int keep_latest_impl(const int64_t* key, const int32_t* t, int64_t n_toke
 
 static int compact_impl(const uint8_t* mask, int64_t n_tokens, void* workspace, size_t workspace_bytes,
                         int32_t* idx_out, int32_t* n_keep_out, const int64_t* range_off,
-                        int64_t n_ranges, int32_t* range_keep_off_out, cudaStream_t st) {
+                        int64_t n_ranges, int32_t* range_keep_off_out, cudaStream_t st, bool ticket_zeroed = false) {
     const int64_t n_blocks = (n_tokens + CB - 1) / CB;
     const size_t need = (size_t)(n_blocks + 2) * sizeof(int32_t);
     SVLN_REQUIRE(workspace && workspace_bytes >= need, SVLN_ERR_NOMEM,
                  "svln_compact_mask: workspace %zu < %zu bytes", workspace_bytes, need);
     int32_t* blk = (int32_t*)workspace;
-    if (n_blocks > 0) {
-        compact_count_kernel<<<(unsigned)n_blocks, 256, 0, st>>>(mask, n_tokens, blk);
+    unsigned* ticket = (unsigned*)(blk + n_blocks + 1);
+    if (n_blocks == 0) {
+        compact_empty_kernel<<<1, 32, 0, st>>>(blk, n_keep_out);
+    } else {
+        if (!ticket_zeroed) SVLN_CUDA(cudaMemsetAsync(ticket, 0, sizeof(unsigned), st));
+        compact_count_scan_kernel<<<(unsigned)n_blocks, 256, 0, st>>>(mask, n_tokens, blk, ticket, n_keep_out);
     }
-    compact_scan_kernel<<<1, 1024, 0, st>>>(blk, n_blocks, n_keep_out);
-    if (n_blocks > 0) {
-        compact_write_kernel<<<(unsigned)n_blocks, 256, 0, st>>>(mask, n_tokens, blk, idx_out);
-    }
-    if (n_ranges > 0 && range_off && range_keep_off_out) {
-        const int64_t n_off = n_ranges + 1;
-        compact_ranges_kernel<<<(unsigned)((n_off + 127) / 128), 128, 0, st>>>(
-            mask, n_tokens, blk, range_off, n_off, range_keep_off_out);
+    const bool ranges = n_ranges > 0 && range_off && range_keep_off_out;
+    const int64_t n_off = ranges ? n_ranges + 1 : 0;
+    const int64_t extra = (n_off + 7) / 8;          // one warp per range boundary
+    if (n_blocks + extra > 0) {
+        compact_write_kernel<<<(unsigned)(n_blocks + extra), 256, 0, st>>>(mask, n_tokens, blk, idx_out, (int)n_blocks,
+                                                                          range_off, n_off, range_keep_off_out);
     }
     return check_launch("compact kernels");
 }
@@ -567,7 +594,7 @@ int svln_voxel_keys(const float* depth, const float* pose, const float* intr, in
     if (n_frames == 0) return SVLN_OK;
     SVLN_REQUIRE(n_frames <= 0x7FFFFFFF, SVLN_ERR_RANGE, "svln_voxel_keys: too many frames");
     voxel_keys_kernel<<<(unsigned)n_frames, 256, 0, (cudaStream_t)stream>>>(
-        depth, pose, intr, H, W, G, voxel_size, max_depth, key_out);
+        depth, pose, intr, H, W, G, voxel_size, max_depth, key_out, PruneSetup{});
     return check_launch("voxel_keys_kernel");
 }
 
@@ -673,16 +700,17 @@ int svln_voxel_prune(const float* depth, const float* pose, const float* intr, c
     int64_t* seg_off = (int64_t*)(ws + w.seg_off_off);
     int64_t* range_off = (int64_t*)(ws + w.range_off_off);
 
-    int rc = svln_voxel_keys(depth, pose, intr, (int64_t)n_streams * n_frames, H, W, G, voxel_size,
-                             max_depth, key_out, stream);
-    if (rc) return rc;
-    fill_frame_t_kernel<<<(unsigned)((n_tokens + 255) / 256), 256, 0, st>>>(t_arr, n_tokens, (int)tpf,
-                                                                            n_frames);
-    segment_offsets_kernel<<<(unsigned)((n_segments + 1 + 127) / 128), 128, 0, st>>>(
-        seg_off, n_segments, pps, stream_tokens, seg_tokens);
-    fill_offsets_kernel<<<(unsigned)((n_streams + 1 + 127) / 128), 128, 0, st>>>(range_off, n_streams,
-                                                                                  stream_tokens, n_tokens);
-    rc = check_launch("prune setup kernels");
+    // keys + frame times + segment / range offsets + the compaction's arrival counter: one launch
+    const int64_t n_blocks = (n_tokens + CB - 1) / CB;
+    PruneSetup su;
+    su.t_out = t_arr; su.seg_off = seg_off; su.range_off = range_off;
+    su.ticket = (unsigned*)((int32_t*)workspace + n_blocks + 1);
+    su.n_segments = n_segments; su.n_streams = n_streams; su.stream_tokens = stream_tokens; su.seg_tokens = seg_tokens;
+    su.n_tokens = n_tokens; su.pps = pps; su.n_frames = n_frames;
+    SVLN_REQUIRE((int64_t)n_streams * n_frames <= 0x7FFFFFFF, SVLN_ERR_RANGE, "svln_voxel_prune: too many frames");
+    voxel_keys_kernel<<<(unsigned)((int64_t)n_streams * n_frames), 256, 0, st>>>(depth, pose, intr, H, W, G, voxel_size,
+                                                                                 max_depth, key_out, su);
+    int rc = check_launch("voxel_keys_kernel");
     if (rc) return rc;
     // uniform fast path (no binary search) when every segment has the same length
     const int64_t uniform = (n_frames % per == 0) ? seg_tokens : 0;
@@ -691,8 +719,10 @@ int svln_voxel_prune(const float* depth, const float* pose, const float* intr, c
     if (rc) return rc;
     rc = svln_frame_threshold(mask_out, (int64_t)n_streams * n_frames, (int)tpf, min_keep, stream);
     if (rc) return rc;
+    // the global-table dedup path memsets the head of the workspace (the ticket lives there): re-zero it in that case
     rc = compact_impl(mask_out, n_tokens, workspace, w.head_bytes, idx_out, n_keep_out, range_off,
-                      stream_keep_off_out ? n_streams : 0, stream_keep_off_out, st);
+                      stream_keep_off_out ? n_streams : 0, stream_keep_off_out, st,
+                      /*ticket_zeroed=*/seg_tokens <= SMEM_DEDUP_MAX_TOKENS);
     if (rc) return rc;
     if (feat && feat_out) rc = gather_impl(feat, (int64_t)D * 2, idx_out, n_keep_out, n_tokens, feat_out, st);
     return rc;
