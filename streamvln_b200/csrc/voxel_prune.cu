@@ -318,7 +318,7 @@ __device__ __forceinline__ void scan_block_counts(int32_t* blk_cnt, int64_t n_bl
     constexpr int NW = NT / 32;
     for (int64_t b0 = 0; b0 < n_blocks; b0 += NT) {
         const int64_t b = b0 + threadIdx.x;
-        const int v = b < n_blocks ? __ldcg(blk_cnt + b) : 0;
+        const int v = b < n_blocks ? (int)ld_cg_u32(blk_cnt + b) : 0;   // written by other CTAs of this launch
         int inc = v;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
