@@ -61,7 +61,8 @@ class VLNEvaluator(_Agent):
     def __init__(self, config_path: Optional[str] = None, split: str = "val_seen", env_num: int = 8, output_path: str = None,
                  model: Any = None, tokenizer: Any = None, epoch: int = 0, args=None, *,
                  env_factory: Optional[Callable[[], Any]] = None, sim_sensors=None,
-                 filter_depth: Optional[Callable] = None, rank: Optional[int] = None):
+                 filter_depth: Optional[Callable] = None, rank: Optional[int] = None, episode_seed=None):
+        self.episode_seed, self._rng = episode_seed, None
         self.split, self.env_num, self.output_path, self.epoch, self.config_path = split, env_num, output_path, epoch, config_path or ""
         if env_factory is None:
             env_factory, sim_sensors = self._habitat_factory(config_path, split)
@@ -99,7 +100,7 @@ class VLNEvaluator(_Agent):
         return (lambda: habitat.Env(config=config)), config.habitat.simulator.agents.main_agent.sim_sensors
 
     def _conjunction(self) -> str:
-        return random.choice(self.conjunctions)                             # :424
+        return (self._rng or random).choice(self.conjunctions)              # :424 (the reference draws from the global RNG)
 
     def _get_rank(self) -> int:
         if self._rank is not None:
@@ -147,7 +148,7 @@ class VLNEvaluator(_Agent):
                     if self._get_rank() == 0:
                         sucs.append(res["success"]); spls.append(res["spl"]); oss.append(res["os"]); ones.append(res["ne"])
         os.makedirs(self.output_path, exist_ok=True)
-        self.episode_seconds: List[float] = []
+        self._finished: List[tuple] = []
         for scene in sorted(scene_episode_dict.keys()):
             episodes = scene_episode_dict[scene]
             scene_id = scene.split("/")[-2]
@@ -157,6 +158,7 @@ class VLNEvaluator(_Agent):
                 if [scene_id, episode_id, episode_instruction] in done_res:
                     continue
                 metrics, step_id = self._run_episode(env, episode, idx)
+                self._finished.append((scene_id, episode_id))
                 sucs.append(metrics["success"]); spls.append(metrics["spl"])
                 oss.append(metrics["oracle_success"]); ones.append(metrics["distance_to_goal"])
                 result = {"scene_id": scene_id, "episode_id": episode_id, "success": metrics["success"], "spl": metrics["spl"],
@@ -170,9 +172,22 @@ class VLNEvaluator(_Agent):
                 torch.tensor(len(sucs)).to(dev))
 
     def _run_episode(self, env, episode, idx: int):
-        """One episode (:225-364).  Raw observations are buffered; a frame is preprocessed the first time a model call
-        selects it."""
+        """One episode, one model call at a time (the reference's schedule)."""
+        gen = self._episode(env, episode, idx)
+        req = next(gen)
+        try:
+            while True:
+                req = gen.send(self.model.generate(**req))
+        except StopIteration as done:
+            return done.value
+
+    def _episode(self, env, episode, idx: int):
+        """One episode (:225-364) as a generator: yields the kwargs of each `model.generate` call and is sent its output, so
+        that several episodes can be in flight on one model replica (`ConcurrentEvaluator`).  Raw observations are buffered;
+        a frame is preprocessed the first time a model call selects it."""
         self._init_state()
+        if self.episode_seed is not None:          # per-episode prompt RNG: the schedule of other episodes cannot shift it
+            self._rng = random.Random(f"{self.episode_seed}/{episode.scene_id}/{episode.episode_id}")
         self.model.reset_episode(idx) if hasattr(self.model, "reset_episode") else self.model.reset_for_env(idx)
         env.current_episode = episode
         observations = env.reset()
@@ -223,11 +238,11 @@ class VLNEvaluator(_Agent):
                 intrinsics = torch.stack([K for _ in sel]).unsqueeze(0)
                 if not images.is_cuda and self.device.type == "cuda":
                     images = images.pin_memory().to(self.device, non_blocking=True)
-                outputs = self.model.generate(inputs=input_ids, images=images, depths=depths, poses=poses, intrinsics=intrinsics,
-                                              env_id=idx, time_ids=[list(time_ids)], task_type=[0], frame_ids=list(sel),
-                                              episode_id=self.episode_id, do_sample=False, num_beams=1,
-                                              max_new_tokens=self.max_new_tokens, use_cache=True, return_dict_in_generate=True,
-                                              past_key_values=past_key_values)
+                outputs = yield dict(inputs=input_ids, images=images, depths=depths, poses=poses, intrinsics=intrinsics,
+                                     env_id=idx, time_ids=[list(time_ids)], task_type=[0], frame_ids=list(sel),
+                                     episode_id=self.episode_id, do_sample=False, num_beams=1,
+                                     max_new_tokens=self.max_new_tokens, use_cache=True, return_dict_in_generate=True,
+                                     past_key_values=past_key_values)
                 self.past_key_values = None
                 action_seq, _ = self.finish(outputs)                          # keeps ids, decodes, parses; [] -> [0] (:341-342)
                 output_ids, past_key_values = self.output_ids, outputs.past_key_values
@@ -240,6 +255,89 @@ class VLNEvaluator(_Agent):
         return env.get_metrics(), step_id
 
 
+class ConcurrentEvaluator:
+    """`eval_action` with E simulators per rank: the rank's episodes (`episodes[idx::env_num]` of every scene, in the
+    reference's order) are dealt to E slots, each slot walks its episode with its own simulator and agent state, and the
+    model turns that are due at the same time go through ONE packed `model.generate_batch` - on a B200 64 concurrent
+    streams cost ~3x less GPU time per env step than one (profiles/README.md, `batched`).  Per episode the calls, the
+    actions and the result row are those of the sequential loop (with `episode_seed` the prompt RNG is per episode, so the
+    prompts match too); result.json rows appear in completion order."""
+
+    def __init__(self, n_slots: int, **evaluator_kw):
+        self.n_slots = n_slots
+        evaluator_kw.setdefault("episode_seed", 0)
+        self.slots = [VLNEvaluator(**evaluator_kw) for _ in range(n_slots)]
+        self.model = evaluator_kw["model"]
+        self.batch_sizes: List[int] = []
+
+    def eval_action(self, idx: int):
+        lead = self.slots[0]
+        envs = [ev.env_factory() for ev in self.slots]
+        scene_episode_dict = {}
+        for episode in envs[0].episodes:
+            scene_episode_dict.setdefault(episode.scene_id, []).append(episode)
+        sucs, spls, oss, ones, done_res = [], [], [], [], []
+        result_path = os.path.join(lead.output_path, "result.json")
+        if os.path.exists(result_path):
+            with open(result_path) as f:
+                for line in f.readlines():
+                    res = json.loads(line)
+                    if "scene_id" not in res:
+                        continue
+                    done_res.append([res["scene_id"], res["episode_id"], res["episode_instruction"]])
+                    if lead._get_rank() == 0:
+                        sucs.append(res["success"]); spls.append(res["spl"]); oss.append(res["os"]); ones.append(res["ne"])
+        os.makedirs(lead.output_path, exist_ok=True)
+        queue = []
+        for scene in sorted(scene_episode_dict.keys()):
+            for episode in scene_episode_dict[scene][idx::lead.env_num]:
+                text = episode.instruction.instruction_text if "objectnav" not in lead.config_path else episode.object_category
+                if [scene.split("/")[-2], episode.episode_id, text] not in done_res:
+                    queue.append((scene.split("/")[-2], episode, text))
+        live = {}                                  # slot -> (generator, pending request, scene_id, episode, text)
+
+        def start(j):
+            while queue:
+                scene_id, episode, text = queue.pop(0)
+                gen = self.slots[j]._episode(envs[j], episode, j)
+                try:
+                    live[j] = (gen, next(gen), scene_id, episode, text)
+                    return
+                except StopIteration as done:          # an episode that is over before its first model turn
+                    finish(j, scene_id, episode, text, done.value)
+
+        def finish(j, scene_id, episode, text, value):
+            metrics, step_id = value
+            sucs.append(metrics["success"]); spls.append(metrics["spl"])
+            oss.append(metrics["oracle_success"]); ones.append(metrics["distance_to_goal"])
+            row = {"scene_id": scene_id, "episode_id": episode.episode_id, "success": metrics["success"], "spl": metrics["spl"],
+                   "os": metrics["oracle_success"], "ne": metrics["distance_to_goal"], "steps": step_id, "episode_instruction": text}
+            with open(result_path, "a") as f:
+                f.write(json.dumps(row) + "\n")
+
+        for j in range(self.n_slots):
+            start(j)
+        while live:
+            order = sorted(live)
+            reqs = [live[j][1] for j in order]
+            outs = self.model.generate_batch(reqs) if len(reqs) > 1 or not hasattr(self.model, "generate") \
+                else [self.model.generate(**reqs[0])]
+            self.batch_sizes.append(len(reqs))
+            for j, out in zip(order, outs):
+                gen, _, scene_id, episode, text = live[j]
+                try:
+                    live[j] = (gen, gen.send(out), scene_id, episode, text)
+                except StopIteration as done:
+                    del live[j]
+                    finish(j, scene_id, episode, text, done.value)
+                    start(j)
+        for env in envs:
+            env.close()
+        dev = lead.device
+        return (torch.tensor(sucs).to(dev), torch.tensor(spls).to(dev), torch.tensor(oss).to(dev), torch.tensor(ones).to(dev),
+                torch.tensor(len(sucs)).to(dev))
+
+
 def evaluate(model, tokenizer, args, **evaluator_kw):
     """streamvln_eval.py:536-581: one evaluator per rank, `eval_action(rank)`, all_gather of the episode counts and of the
     four metric vectors, the averaged summary appended to result.json by rank 0.  Returns the summary dict."""
@@ -248,10 +346,15 @@ def evaluate(model, tokenizer, args, **evaluator_kw):
     on = dist.is_available() and dist.is_initialized()
     world_size, rank = (dist.get_world_size(), dist.get_rank()) if on else (1, 0)
     model.eval()
-    model.reset(world_size)
-    evaluator = VLNEvaluator(config_path=getattr(args, "habitat_config_path", None), split=getattr(args, "eval_split", "val_unseen"),
-                             env_num=world_size, output_path=args.output_path, model=model, tokenizer=tokenizer, epoch=0, args=args,
-                             **evaluator_kw)
+    n_concurrent = int(getattr(args, "concurrent_episodes", 1) or 1)      # > 1: E simulators per rank, packed model turns
+    kw = dict(config_path=getattr(args, "habitat_config_path", None), split=getattr(args, "eval_split", "val_unseen"),
+              env_num=world_size, output_path=args.output_path, model=model, tokenizer=tokenizer, epoch=0, args=args, **evaluator_kw)
+    if n_concurrent > 1:
+        model.reset(n_concurrent)
+        evaluator = ConcurrentEvaluator(n_concurrent, **kw)
+    else:
+        model.reset(world_size)
+        evaluator = VLNEvaluator(**kw)
     sucs, spls, oss, ones, ep_num = evaluator.eval_action(rank)
     vecs = [v.to(torch.float64) for v in (sucs, spls, oss, ones)]
     if on:

@@ -123,9 +123,10 @@ class RecordingModel:
     """Fake model: records every `generate(**kw)` and `reset_for_env`, answers with a scripted token sequence whose decoded
     text yields 0..5 actions (so the loop's action queue, its empty-answer STOP rule and odd cadences are all exercised)."""
 
-    def __init__(self, tokenizer):
+    def __init__(self, tokenizer, by_step: bool = False):
         self.tok = tokenizer
-        self.calls, self.resets = [], []
+        self.by_step = by_step            # answers depend on (episode, step) only: independent of the order of the calls
+        self.calls, self.resets, self.batches = [], [], []
         self.tower = SimpleNamespace(image_processor=StampProcessor())
         self.model = SimpleNamespace(num_history=None)
         # StubQwenTokenizer decodes an ordinary id i as the action glyph i % 4 (STOP, forward, left, right)
@@ -164,13 +165,17 @@ class RecordingModel:
             n = 4                                               # model steps land on the window boundaries 32 and 64
         return [((t + j + ep) % 3) + 1 for j in range(n)]
 
+    def generate_batch(self, requests):
+        self.batches.append(len(requests))
+        return [self.generate(**r) for r in requests]
+
     def generate(self, **kw):
         import torch
 
         t = len(self.calls)
         img = kw["images"][0].float()
         views = [[int(round(float(img[v, c, 0, 0]))) for c in range(3)] for v in range(img.shape[0])]
-        acts = self.script(t, views)
+        acts = self.script(views[-1][0] if self.by_step else t, views)
         seq = [i for a in acts for i in self._ids[a]] + [self.tok.im_end]
         self.calls.append(dict(
             inputs=kw["inputs"][0].tolist(), views=views, time_ids=list(kw["time_ids"][0]), env_id=kw["env_id"],

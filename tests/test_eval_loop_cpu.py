@@ -154,3 +154,49 @@ def test_evaluate_gathers_over_two_ranks(gold, tmp_path):
             assert abs(got[r][k] - want[k]) < 1e-9, (k, got[r][k], want[k])
     last = (tmp_path / "result.json").read_text().splitlines()[-1]
     assert json.loads(last[last.index('{"sucs_all"'):])["length"] == 7
+
+
+def _per_episode(model, env_logs):
+    calls = {}
+    for c in model.calls:
+        calls.setdefault(c["views"][-1][1], []).append((c["inputs"], [v[0] for v in c["views"]], c["time_ids"], c["fresh"],
+                                                        c["poses"].tobytes(), c["depths"][-1][::37, ::41].tobytes()))
+    acts = {}
+    for log in env_logs:
+        for e, a in log:
+            acts.setdefault(int(e), []).append(a)
+    return calls, acts
+
+
+@pytest.mark.parametrize("n_slots", [2, 3, 8])
+def test_concurrent_evaluator_equals_the_sequential_loop(tmp_path, n_slots):
+    """E simulators per rank with packed model turns: per episode the model calls (prompt ids, views, time_ids, cache
+    hand-over, geometry), the actions and the result row are those of the one-episode-at-a-time loop."""
+    from streamvln_b200.habitat_eval import ConcurrentEvaluator, VLNEvaluator
+    from streamvln_b200.tokenizer import StubQwenTokenizer
+
+    def make(kind, out):
+        tok = StubQwenTokenizer(152064)
+        model = fake_env.RecordingModel(tok, by_step=True)
+        args = SimpleNamespace(num_frames=32, num_future_steps=4, num_history=8, save_video=False, gpu_preprocess=False)
+        envs = []
+        kw = dict(config_path="config/vln_r2r.yaml", split="val_unseen", env_num=1, output_path=str(out), model=model, tokenizer=tok,
+                  epoch=0, args=args, env_factory=lambda: envs.append(fake_env.FakeEnv()) or envs[-1], sim_sensors=fake_env.fake_sensors(),
+                  filter_depth=lambda d, blur_type=None: d, rank=0, episode_seed=7)
+        ev = VLNEvaluator(**kw) if kind == "seq" else ConcurrentEvaluator(n_slots, **kw)
+        ret = ev.eval_action(0)
+        rows = [json.loads(l) for l in (Path(out) / "result.json").read_text().splitlines()]
+        return model, envs, rows, ret
+
+    ms, es, rs, rets = make("seq", tmp_path / "seq")
+    mc, ec, rc, retc = make("conc", tmp_path / "conc")
+    assert len(ec) == n_slots and all(e.closed for e in ec)
+    cs, as_ = _per_episode(ms, [e.log for e in es])
+    cc, ac = _per_episode(mc, [e.log for e in ec])
+    assert cs == cc and as_ == ac
+    key = lambda r: int(r["episode_id"])
+    assert sorted(rs, key=key) == sorted(rc, key=key)
+    assert sorted(zip(*[v.tolist() for v in rets[:4]])) == sorted(zip(*[v.tolist() for v in retc[:4]])) and int(rets[4]) == int(retc[4]) == 7
+    assert max(mc.batches) == min(n_slots, 7) and sum(mc.batches) <= len(mc.calls)       # single requests go through generate()
+    # every stream of a packed call is a different model slot
+    assert all(0 <= c["env_id"] < n_slots for c in mc.calls)
