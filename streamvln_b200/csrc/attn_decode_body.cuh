@@ -185,7 +185,11 @@ __device__ __forceinline__ void attn_decode_body(const DecodeParams& p, int spli
     float l_run[2] = {0.f, 0.f};
 
     for (int it = 0; it < n_tiles; ++it) {
-        cp_async_wait<PRO - 1>();
+        // tile `it` must have landed.  Rolling ring (PRO = STAGES - 1): the one group that may stay in flight is the tile
+        // requested in the previous iteration (it + STAGES - 2).  FULL ring: a stage is refilled one iteration after it was
+        // consumed, so the newest group IS tile `it` - nothing may stay in flight (waiting with <PRO - 1> consumed splits of
+        // more than STAGES tiles before their last tiles had arrived: two-stream steps, 18 splits of up to 4 tiles).
+        cp_async_wait<FULL ? 0 : PRO - 1>();
         group_sync<BAR_ID>();
         if (it == 0) AD_TRACE(2);
         {   // refill the stage consumed in the previous iteration

@@ -200,8 +200,10 @@ def test_decode_stack_two_streams_at_7b_dims(big, cuda, kv_lens):
             caches.append((c32, c16))
         tok = torch.cat(toks)
         runner = eng._decode_runner([2, 3], True)
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=cuda)
         for step in range(n_steps):
             fed = tok.clone()
+            flush.fill_(step)                         # K/V and weights come from HBM, as in a 28-layer step
             tok = runner.step(tok)
             assert runner.graph.state.stack is not None, "two streams must take the fused stack"
             assert int(tok.min()) >= 0, "a grid barrier of the fused stack timed out"
@@ -219,6 +221,52 @@ def test_decode_stack_two_streams_at_7b_dims(big, cuda, kv_lens):
     finally:
         eng.keep_decode_logits = False
         eng._graphs.clear()
+
+
+def test_decode_stack_is_deterministic_at_full_depth(svln_lib, cuda):
+    """All 28 layers at the 7B shape, two streams (18 attention splits of up to 4 key tiles): the same state decoded four
+    times gives bit-identical logits, and the stack stays close to the launch-per-op path.  Regression test: the in-kernel
+    attention item consumed splits of more than two tiles before their last tiles had landed (`cp.async.wait_group 1` on
+    a ring that refills one iteration late) - invisible with K/V resident in L2 (2 layers), every step with K/V in HBM."""
+    from streamvln_b200.qwen2 import Chunk, Qwen2Config, Qwen2Engine, Qwen2Weights
+
+    cfg = Qwen2Config()
+    w = Qwen2Weights.random(cfg, cuda, seed=0, lm_head_std=0.05, norm_std=0.25)
+    eng = Qwen2Engine(cfg, w, n_env=2, device=cuda)
+    eng.keep_decode_logits = True
+    ctx = [2970, 1733]
+    first = []
+    for b, n in enumerate(ctx):
+        e = _emb(n, cfg.hidden_size, 5 + b, cuda)
+        first.append(eng.forward(e, [Chunk(b, 0, n, n)]).argmax(-1).reshape(1))
+    first = torch.cat(first)
+    forced = None
+
+    def decode(n_stack):
+        eng.STACK_MAX_STREAMS = n_stack
+        eng._graphs.clear()
+        for b, n in enumerate(ctx):
+            eng.arena.lens[b] = n
+        runner = eng._decode_runner([0, 1], True)
+        tok, logs, toks = first.clone(), [], []
+        for i in range(6):
+            tok = runner.step(tok)
+            assert int(tok.min()) >= 0
+            logs.append(runner.last_logits())
+            toks.append(tok.clone())
+            if forced is not None:
+                tok = forced[i]                     # every run feeds the same tokens
+        runner.finish()
+        assert (runner.graph.state.stack is not None) == (n_stack >= 2)
+        return torch.stack(logs), toks
+
+    ref, forced = decode(0)                          # launch-per-op path (svln_gemv / cuBLAS + the small kernels)
+    runs = [decode(2)[0] for _ in range(4)]
+    assert all(torch.equal(runs[0], r) for r in runs[1:]), "the fused two-stream step is not deterministic"
+    rel = float((runs[0] - ref).abs().max() / ref.abs().max())
+    assert rel <= 8e-2, rel                          # 28 layers of bf16 rounding in two different accumulation orders
+    del eng, w
+    torch.cuda.empty_cache()
 
 
 def test_bf16_tie_goes_to_the_lowest_index_on_every_decode_path(big, cuda):
