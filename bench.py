@@ -376,26 +376,29 @@ def batched_block(model, a, dist, device, rank, world):
            "action_hashes": [f"{r.action_hash:016x}" for r in allres]}
     del ev, m_b
     torch.cuda.empty_cache()
-    W = int(getattr(a, "emulate_world", 0) or 0)
-    if W > 1 and world == 1:
+    worlds = [int(x) for x in str(getattr(a, "emulate_world", "") or "").split(",") if x.strip() and int(x) > 1]
+    if worlds and world == 1:
         # Multi-GPU parity check that needs one GPU: run every shard episodes[r::W] of a W-rank job here, one after the
         # other, with the SAME pack compositions a W-rank run has (same priming, so the same graphs replay).  A pack of
         # 64 and a pack of 64 / W give cuBLAS different GEMM shapes, so the N = 1 hashes above are NOT comparable with an
         # N = W run's; these are: `digest` must equal the `action_hash_digest` the W-rank run prints.
-        emu = []
-        for r in range(W):
-            shard = shard_episodes(episodes, r, W)
-            m_s = StreamVLNForCausalLM(cfg, weights=model.weights, vision=model.vision, n_env=len(shard), device=device)
-            ev_s = BatchedEvaluator(m_s, lambda: StubQwenTokenizer(cfg.llm.vocab_size), len(shard), args, {"camera_intrinsic": intrinsic_matrix()})
-            for _ in range(2):
-                run_episodes(ev_s, shard, host_src, resident_source=dev_src)
-            emu += run_episodes(ev_s, shard, host_src, resident_source=dev_src)
-            del ev_s, m_s
-            torch.cuda.empty_cache()
-        emu.sort(key=lambda r: r.episode_id)
-        out["emulated_world"] = {"world": W, "digest": hashlib.sha256(",".join(f"{r.episode_id}:{r.action_hash:016x}" for r in emu).encode()).hexdigest()[:16],
-                                 "action_hashes": [f"{r.action_hash:016x}" for r in emu],
-                                 "note": f"the {W} shards episodes[r::{W}] run one after another on this GPU with a {W}-rank job's pack compositions"}
+        out["emulated_world"] = {}
+        for W in worlds:
+            emu = []
+            for r in range(W):
+                shard = shard_episodes(episodes, r, W)
+                m_s = StreamVLNForCausalLM(cfg, weights=model.weights, vision=model.vision, n_env=len(shard), device=device)
+                ev_s = BatchedEvaluator(m_s, lambda: StubQwenTokenizer(cfg.llm.vocab_size), len(shard), args, {"camera_intrinsic": intrinsic_matrix()})
+                for _ in range(2):
+                    run_episodes(ev_s, shard, host_src, resident_source=dev_src)
+                emu += run_episodes(ev_s, shard, host_src, resident_source=dev_src)
+                del ev_s, m_s
+                torch.cuda.empty_cache()
+            emu.sort(key=lambda r: r.episode_id)
+            out["emulated_world"][str(W)] = {
+                "digest": hashlib.sha256(",".join(f"{r.episode_id}:{r.action_hash:016x}" for r in emu).encode()).hexdigest()[:16],
+                "action_hashes": [f"{r.action_hash:016x}" for r in emu],
+                "note": f"the {W} shards episodes[r::{W}] run one after another on this GPU with a {W}-rank job's pack compositions"}
     return out
 
 
@@ -681,8 +684,8 @@ def main():
     ap.add_argument("--episodes", type=int, default=64, help="total concurrent episodes of the batched block (configs[2])")
     ap.add_argument("--blocks", default="slowfast,batched,kernels,hf,cpu",
                     help="extra blocks measured after the headline arms (kernels / hf / cpu only at N=1)")
-    ap.add_argument("--emulate-world", type=int, default=0,
-                    help="1-GPU runs: also run the batched block's shards of a W-rank job one after another (multi-GPU parity: "
+    ap.add_argument("--emulate-world", default="",
+                    help="1-GPU runs: W or a comma list (2,4,8): also run the batched block's shards of a W-rank job one after another (multi-GPU parity: "
                          "the digest must equal the W-rank run's action_hash_digest)")
     ap.add_argument("--no-micro", action="store_true", help="skip the per-kernel microbenchmarks")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
