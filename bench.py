@@ -189,9 +189,13 @@ def build_agent(device, mode: str, share=None):
     return model, agent
 
 
+LAST_ACTIONS = []      # actions of the most recent run_turns call (hashed by main_ours: ranks must agree)
+
+
 def run_turns(agent, n_turns: int, frames_host, frames_dev, resident: bool, geom=None):
     """n_turns model turns = 4*n_turns env steps through VLNEvaluator.step (the call a user makes)."""
     h2d = d2h = 0
+    del LAST_ACTIONS[:]
     verbose = os.environ.get("SVLN_BENCH_VERBOSE") == "1"
     marks = []
     for ti in range(n_turns):
@@ -208,10 +212,11 @@ def run_turns(agent, n_turns: int, frames_host, frames_dev, resident: bool, geom
                 kw = dict(depth=geom["depth"][s % len(geom["depth"])], pose=geom["pose"][s % len(geom["pose"])],
                           intrinsic=geom["intr"][0])
             if resident:
-                agent.step(0, None, INSTRUCTION, run_model=(k == 0), preprocessed=frames_dev[i] if k == 0 else None, **kw)
+                acts = agent.step(0, None, INSTRUCTION, run_model=(k == 0), preprocessed=frames_dev[i] if k == 0 else None, **kw)[0]
             else:
-                agent.step(0, frames_host[i], INSTRUCTION, run_model=(k == 0), **kw)
+                acts = agent.step(0, frames_host[i], INSTRUCTION, run_model=(k == 0), **kw)[0]
             if k == 0:
+                LAST_ACTIONS.extend(acts or [])
                 h2d += getattr(agent, "h2d_bytes", 0)
                 d2h += getattr(agent, "d2h_bytes", 0)
                 if geom is not None and not resident:
@@ -482,7 +487,9 @@ def main_ours(a):
     svln_build.build()
     blocks = set(a.blocks.split(","))
     model, agent = build_agent(device, a.mode)
-    rng = np.random.default_rng(1234 + rank)
+    # every rank streams the SAME synthetic episode (same frames, same random-init weights): the action sequences of
+    # the timed regions must then be identical on every GPU - `stream_check` below
+    rng = np.random.default_rng(1234)
     frames_host = rng.integers(0, 255, size=(64, 480, 640, 3), dtype=np.uint8)
     geom = None
     if a.mode == "slowfast":
@@ -507,6 +514,9 @@ def main_ours(a):
         sampler.start()
     ms, launches, _, _ = timed(agent, model, KT, frames_host, frames_dev, True, dist, device, geom)
     clocks = sampler.stop() if rank == 0 else None
+    from streamvln_b200.scheduler import hash_actions
+
+    hash_res, n_act = hash_actions(LAST_ACTIONS), len(LAST_ACTIONS)
     # ---- a few windows once more with CUDA events around the dominant kernels (events cannot be recorded inside a
     #      replayed CUDA graph, so this pass launches the kernels eagerly)
     model.engine.prof = {}
@@ -517,6 +527,15 @@ def main_ours(a):
     agent.reset_memory()
     run_turns(agent, WT, frames_host, frames_dev, False, geom)
     ms_e2e, _, h2d, d2h = timed(agent, model, KT, frames_host, frames_dev, False, dist, device, geom)
+    hash_e2e = hash_actions(LAST_ACTIONS)
+    hashes = torch.tensor([hash_res, hash_e2e], dtype=torch.int64, device=device)
+    all_h = [hashes.clone() for _ in range(world)]
+    if dist is not None:
+        dist.all_gather(all_h, hashes)
+    stream_check = {"resident_action_hash": f"{hash_res:016x}", "e2e_action_hash": f"{hash_e2e:016x}", "actions": n_act,
+                    "e2e_equals_resident": hash_e2e == hash_res,     # GPU image processor == PIL, same steps of the same episode
+                    "ranks_agree": all(bool(torch.equal(h, hashes)) for h in all_h), "ranks": world,
+                    "note": "every rank streams the same synthetic episode with the same random-init weights"}
     steps_total = K * ENV_STEPS_PER_STEP * world
     value = steps_total / (ms / 1e3)
     e2e = steps_total / (ms_e2e / 1e3)
@@ -559,6 +578,7 @@ def main_ours(a):
         "e2e": {"value": round(e2e, 3), "unit": UNIT, "h2d_bytes_per_step": int(h2d / K) * world, "d2h_bytes_per_step": int(d2h / K) * world,
                 "ms_per_step": round(ms_e2e / K, 3)},
         "gpu_launches": int(launches),
+        "stream_check": stream_check,
         "roofline": roof,
         "roofline_prefill": roof_prefill,
         "clocks": clocks,
