@@ -75,13 +75,13 @@ def install_stubs():
     sys.modules["llava.model.multimodal_resampler.qformer"] = q
 
 
-def run_reference(idx: int, env_num: int, out_dir: str, seed: int = 0):
+def run_reference(idx: int, env_num: int, out_dir: str, seed: int = 0, num_history=8):
     import streamvln_eval as ref                       # the reference module, unmodified
     from streamvln_b200.tokenizer import StubQwenTokenizer
 
     tok = StubQwenTokenizer(152064)
     model = fake_env.RecordingModel(tok)
-    args = SimpleNamespace(num_frames=32, num_future_steps=4, num_history=8, save_video=False)
+    args = SimpleNamespace(num_frames=32, num_future_steps=4, num_history=num_history, save_video=False)
     random.seed(seed)
     envs = []
     ref.Env = lambda config=None: envs.append(fake_env.FakeEnv()) or envs[-1]
@@ -143,5 +143,9 @@ if __name__ == "__main__":
         blob.update(pack(r, "resume"))
         blob["resume_prefill"] = np.array([l.encode() for l in first_rows[:3]])
         print("resumed:", len(r["model"].calls), "model calls, rows on disk", len(r["rows"]), "returned n", r["n"])
+    with tempfile.TemporaryDirectory() as d:                 # num_history=None: the history slice steps by num_future_steps (:314-315)
+        r = run_reference(0, 1, d, num_history=None)
+        blob.update(pack(r, "nohist"))
+        print("num_history=None:", len(r["model"].calls), "model calls, views per call up to", max(len(c["views"]) for c in r["model"].calls))
     np.savez_compressed(OUT / "ref_eval_loop.npz", **blob)
     print("wrote", OUT / "ref_eval_loop.npz", (OUT / "ref_eval_loop.npz").stat().st_size, "bytes")

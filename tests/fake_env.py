@@ -23,7 +23,7 @@ def make_episodes() -> List[SimpleNamespace]:
     eps = []
     spec = [("sceneB", 3, "go down the hall and stop by the plant", 70), ("sceneA", 1, "walk past the sofa", 37),
             ("sceneA", 2, "turn left at the stairs", 9), ("sceneB", 4, "enter the kitchen", 33),
-            ("sceneA", 5, "leave the room", 64), ("sceneB", 6, "find the red chair", 21), ("sceneA", 7, "stop at the door", 5)]
+            ("sceneA", 5, "leave the room", 66), ("sceneB", 6, "find the red chair", 21), ("sceneA", 7, "stop at the door", 5)]
     for scene, eid, text, cap in spec:
         eps.append(SimpleNamespace(scene_id=f"data/scene_datasets/mp3d/{scene}/{scene}.glb", episode_id=str(eid),
                                    instruction=SimpleNamespace(instruction_text=text), max_steps=cap))

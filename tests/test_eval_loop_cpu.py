@@ -23,13 +23,13 @@ import fake_env  # noqa: E402
 GOLD = Path(__file__).resolve().parent / "golden"
 
 
-def _run(idx, env_num, out_dir, rank=0):
+def _run(idx, env_num, out_dir, rank=0, num_history=8):
     from streamvln_b200.habitat_eval import VLNEvaluator
     from streamvln_b200.tokenizer import StubQwenTokenizer
 
     tok = StubQwenTokenizer(152064)
     model = fake_env.RecordingModel(tok)
-    args = SimpleNamespace(num_frames=32, num_future_steps=4, num_history=8, save_video=False, gpu_preprocess=False)
+    args = SimpleNamespace(num_frames=32, num_future_steps=4, num_history=num_history, save_video=False, gpu_preprocess=False)
     random.seed(0)
     envs = []
     ev = VLNEvaluator(config_path="config/vln_r2r.yaml", split="val_unseen", env_num=env_num, output_path=str(out_dir), model=model,
@@ -76,7 +76,7 @@ def gold():
 def test_fixture_covers_the_loop(gold):
     z = gold
     assert z["w1r0_row_episode"].tolist() == [1, 2, 5, 7, 3, 4, 6]            # scenes sorted, dataset order inside a scene
-    assert z["w1r0_row_steps"].tolist()[2] == 64 and z["w1r0_row_steps"].tolist()[4] == 70      # two windows crossed
+    assert z["w1r0_row_steps"].tolist()[2] == 66 and z["w1r0_row_steps"].tolist()[4] == 70      # two windows crossed
     assert 9 in z["w1r0_n_views"].tolist()                                    # a window start with 8 history views
     assert set(z["w1r0_dtypes"].tolist()) == {b"torch.bfloat16"}
     assert z["w2r0_row_episode"].tolist() == [1, 5, 3, 6] and z["w2r1_row_episode"].tolist() == [2, 7, 4]
@@ -94,6 +94,12 @@ def test_episode_sharding_is_pinned(gold, tmp_path, rank):
 def test_resume_from_result_json_is_pinned(gold, tmp_path):
     (tmp_path / "result.json").write_text("\n".join(l.decode() for l in gold["resume_prefill"].tolist()) + "\n")
     _check(gold, "resume", *_run(0, 1, tmp_path))
+
+
+def test_history_slice_without_num_history_is_pinned(gold, tmp_path):
+    """args.num_history = None: every num_future_steps-th past frame becomes a history view (streamvln_eval.py:314-315)."""
+    assert gold["nohist_n_views"].max() == 17 and gold["w1r0_n_views"].max() == 9      # step 64: frames 0, 4, ..., 60 + the current one (8 + 1 with num_history = 8)
+    _check(gold, "nohist", *_run(0, 1, tmp_path, num_history=None))
 
 
 def test_only_selected_frames_are_preprocessed(tmp_path):

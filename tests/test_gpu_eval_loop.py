@@ -46,7 +46,7 @@ def test_driver_gpu_processors_equal_host_processors(svln_lib, cuda, tmp_path):
     b = _walk(cuda, tmp_path / "host", False)
     assert a[2] == b[2] and a[1] == b[1] and a[0] == b[0]
     assert a[0]["length"] == 7 and len(a[1]) == 7 and all(r["steps"] >= 1 for r in a[1])
-    assert sorted(r["steps"] for r in a[1]) == [5, 9, 21, 33, 37, 64, 70]     # the step caps: two window boundaries crossed
+    assert sorted(r["steps"] for r in a[1]) == [5, 9, 21, 33, 37, 66, 70]     # the step caps: two window boundaries crossed
 
 
 def test_driver_runs_the_slowfast_mode(svln_lib, cuda, tmp_path):
@@ -60,5 +60,5 @@ def test_driver_with_concurrent_simulators(svln_lib, cuda, tmp_path, mode):
     and the job reports the same episodes as the sequential driver (token-level equality of packed and single streams is
     bounded in tests/test_gpu_batched.py)."""
     res, rows, _ = _walk(cuda, tmp_path / "conc", True, mode=mode, concurrent=3)
-    assert res["length"] == 7 and sorted(r["steps"] for r in rows) == [5, 9, 21, 33, 37, 64, 70]
+    assert res["length"] == 7 and sorted(r["steps"] for r in rows) == [5, 9, 21, 33, 37, 66, 70]
     assert sorted(int(r["episode_id"]) for r in rows) == [1, 2, 3, 4, 5, 6, 7]
