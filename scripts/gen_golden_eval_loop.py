@@ -75,7 +75,7 @@ def install_stubs():
     sys.modules["llava.model.multimodal_resampler.qformer"] = q
 
 
-def run_reference(idx: int, env_num: int, out_dir: str, seed: int = 0, num_history=8):
+def run_reference(idx: int, env_num: int, out_dir: str, seed: int = 0, num_history=8, config_path="config/vln_r2r.yaml"):
     import streamvln_eval as ref                       # the reference module, unmodified
     from streamvln_b200.tokenizer import StubQwenTokenizer
 
@@ -86,7 +86,7 @@ def run_reference(idx: int, env_num: int, out_dir: str, seed: int = 0, num_histo
     envs = []
     ref.Env = lambda config=None: envs.append(fake_env.FakeEnv()) or envs[-1]
     with contextlib.redirect_stdout(io.StringIO()), contextlib.redirect_stderr(io.StringIO()):
-        ev = ref.VLNEvaluator(config_path="config/vln_r2r.yaml", split="val_unseen", env_num=env_num, output_path=out_dir,
+        ev = ref.VLNEvaluator(config_path=config_path, split="val_unseen", env_num=env_num, output_path=out_dir,
                               model=model, tokenizer=tok, epoch=0, args=args)
         ev.device = torch.device("cpu")                  # the reference hard-codes cuda (streamvln_eval.py:53)
         sucs, spls, oss, ones, n = ev.eval_action(idx)
@@ -147,5 +147,9 @@ if __name__ == "__main__":
         r = run_reference(0, 1, d, num_history=None)
         blob.update(pack(r, "nohist"))
         print("num_history=None:", len(r["model"].calls), "model calls, views per call up to", max(len(c["views"]) for c in r["model"].calls))
+    with tempfile.TemporaryDirectory() as d:                 # an objectnav config: result rows carry the object category (:221)
+        r = run_reference(0, 1, d, config_path="config/objectnav_hm3d.yaml")
+        blob.update(pack(r, "objnav"))
+        print("objectnav:", [x["episode_instruction"] for x in r["rows"]][:3])
     np.savez_compressed(OUT / "ref_eval_loop.npz", **blob)
     print("wrote", OUT / "ref_eval_loop.npz", (OUT / "ref_eval_loop.npz").stat().st_size, "bytes")

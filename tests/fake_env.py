@@ -26,7 +26,7 @@ def make_episodes() -> List[SimpleNamespace]:
             ("sceneA", 5, "leave the room", 66), ("sceneB", 6, "find the red chair", 21), ("sceneA", 7, "stop at the door", 5)]
     for scene, eid, text, cap in spec:
         eps.append(SimpleNamespace(scene_id=f"data/scene_datasets/mp3d/{scene}/{scene}.glb", episode_id=str(eid),
-                                   instruction=SimpleNamespace(instruction_text=text), max_steps=cap))
+                                   instruction=SimpleNamespace(instruction_text=text), object_category=f"category{eid}", max_steps=cap))
     return eps
 
 

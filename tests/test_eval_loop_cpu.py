@@ -23,7 +23,7 @@ import fake_env  # noqa: E402
 GOLD = Path(__file__).resolve().parent / "golden"
 
 
-def _run(idx, env_num, out_dir, rank=0, num_history=8):
+def _run(idx, env_num, out_dir, rank=0, num_history=8, config_path="config/vln_r2r.yaml"):
     from streamvln_b200.habitat_eval import VLNEvaluator
     from streamvln_b200.tokenizer import StubQwenTokenizer
 
@@ -32,7 +32,7 @@ def _run(idx, env_num, out_dir, rank=0, num_history=8):
     args = SimpleNamespace(num_frames=32, num_future_steps=4, num_history=num_history, save_video=False, gpu_preprocess=False)
     random.seed(0)
     envs = []
-    ev = VLNEvaluator(config_path="config/vln_r2r.yaml", split="val_unseen", env_num=env_num, output_path=str(out_dir), model=model,
+    ev = VLNEvaluator(config_path=config_path, split="val_unseen", env_num=env_num, output_path=str(out_dir), model=model,
                       tokenizer=tok, epoch=0, args=args, env_factory=lambda: envs.append(fake_env.FakeEnv()) or envs[-1],
                       sim_sensors=fake_env.fake_sensors(), filter_depth=lambda d, blur_type=None: d, rank=rank)
     ret = ev.eval_action(idx)
@@ -100,6 +100,12 @@ def test_history_slice_without_num_history_is_pinned(gold, tmp_path):
     """args.num_history = None: every num_future_steps-th past frame becomes a history view (streamvln_eval.py:314-315)."""
     assert gold["nohist_n_views"].max() == 17 and gold["w1r0_n_views"].max() == 9      # step 64: frames 0, 4, ..., 60 + the current one (8 + 1 with num_history = 8)
     _check(gold, "nohist", *_run(0, 1, tmp_path, num_history=None))
+
+
+def test_objectnav_rows_are_pinned(gold, tmp_path):
+    """'objectnav' in the config path: result rows (and the resume key) carry the episode's object category (:221)."""
+    assert gold["objnav_row_instruction"].tolist()[0] == b"category1"
+    _check(gold, "objnav", *_run(0, 1, tmp_path, config_path="config/objectnav_hm3d.yaml"))
 
 
 def test_only_selected_frames_are_preprocessed(tmp_path):
