@@ -54,6 +54,26 @@ def _load_filter_depth():
         return (lambda d, blur_type=None: d), "identity (depth_camera_filtering is not installed)"
 
 
+def _read_result_rows(path: str):
+    """Episode rows of a result.json (one JSON object per line).  `evaluate` appends its summary WITHOUT a newline
+    (streamvln_eval.py:580-581), so the first row of a resumed run shares a line with it: every object on a line is read,
+    summary objects (no `scene_id`) are skipped."""
+    rows, dec = [], json.JSONDecoder()
+    if not os.path.exists(path):
+        return rows
+    with open(path) as f:
+        for line in f:
+            i, line = 0, line.strip()
+            while i < len(line):
+                obj, j = dec.raw_decode(line, i)
+                i = j
+                while i < len(line) and line[i].isspace():
+                    i += 1
+                if "scene_id" in obj:
+                    rows.append(obj)
+    return rows
+
+
 class VLNEvaluator(_Agent):
     """Drop-in for the Habitat evaluator class of streamvln/streamvln_eval.py:44-380 (same constructor keywords; the
     simulator and its sensor config can be injected)."""
@@ -138,15 +158,10 @@ class VLNEvaluator(_Agent):
         sucs, spls, oss, ones = [], [], [], []
         done_res = []
         result_path = os.path.join(self.output_path, "result.json")
-        if os.path.exists(result_path):                                     # resume (:205-216)
-            with open(result_path) as f:
-                for line in f.readlines():
-                    res = json.loads(line)
-                    if "scene_id" not in res:                               # the summary line `evaluate` appends
-                        continue
-                    done_res.append([res["scene_id"], res["episode_id"], res["episode_instruction"]])
-                    if self._get_rank() == 0:
-                        sucs.append(res["success"]); spls.append(res["spl"]); oss.append(res["os"]); ones.append(res["ne"])
+        for res in _read_result_rows(result_path):                          # resume (:205-216)
+            done_res.append([res["scene_id"], res["episode_id"], res["episode_instruction"]])
+            if self._get_rank() == 0:
+                sucs.append(res["success"]); spls.append(res["spl"]); oss.append(res["os"]); ones.append(res["ne"])
         os.makedirs(self.output_path, exist_ok=True)
         self._finished: List[tuple] = []
         for scene in sorted(scene_episode_dict.keys()):
@@ -278,15 +293,10 @@ class ConcurrentEvaluator:
             scene_episode_dict.setdefault(episode.scene_id, []).append(episode)
         sucs, spls, oss, ones, done_res = [], [], [], [], []
         result_path = os.path.join(lead.output_path, "result.json")
-        if os.path.exists(result_path):
-            with open(result_path) as f:
-                for line in f.readlines():
-                    res = json.loads(line)
-                    if "scene_id" not in res:
-                        continue
-                    done_res.append([res["scene_id"], res["episode_id"], res["episode_instruction"]])
-                    if lead._get_rank() == 0:
-                        sucs.append(res["success"]); spls.append(res["spl"]); oss.append(res["os"]); ones.append(res["ne"])
+        for res in _read_result_rows(result_path):
+            done_res.append([res["scene_id"], res["episode_id"], res["episode_instruction"]])
+            if lead._get_rank() == 0:
+                sucs.append(res["success"]); spls.append(res["spl"]); oss.append(res["os"]); ones.append(res["ne"])
         os.makedirs(lead.output_path, exist_ok=True)
         queue = []
         for scene in sorted(scene_episode_dict.keys()):

@@ -212,3 +212,14 @@ def test_concurrent_evaluator_equals_the_sequential_loop(tmp_path, n_slots):
     assert max(mc.batches) == min(n_slots, 7) and sum(mc.batches) <= len(mc.calls)       # single requests go through generate()
     # every stream of a packed call is a different model slot
     assert all(0 <= c["env_id"] < n_slots for c in mc.calls)
+
+
+def test_resume_after_a_finished_run(gold, tmp_path):
+    """`evaluate` appends its summary without a newline (streamvln_eval.py:580-581): a later resume finds the next row on
+    the same line.  Every episode of the finished run is recognised as done."""
+    _run(0, 1, tmp_path)
+    with open(tmp_path / "result.json", "a") as f:
+        f.write(json.dumps({"sucs_all": 0.5, "spls_all": 0.1, "oss_all": 0.5, "ones_all": 1.0, "length": 7}))
+    model, env, rows, ret = _run(0, 1, tmp_path)
+    assert len(model.calls) == 0 and env.log == [] and int(ret[4]) == 7
+    assert np.array_equal(np.array([v.tolist() for v in ret[:4]], np.float64), gold["w1r0_ret"])
