@@ -223,3 +223,23 @@ def test_resume_after_a_finished_run(gold, tmp_path):
     model, env, rows, ret = _run(0, 1, tmp_path)
     assert len(model.calls) == 0 and env.log == [] and int(ret[4]) == 7
     assert np.array_equal(np.array([v.tolist() for v in ret[:4]], np.float64), gold["w1r0_ret"])
+
+
+def test_concurrent_evaluator_resumes(gold, tmp_path):
+    """result.json already holds three finished episodes: the concurrent driver runs the other four and returns all seven."""
+    from streamvln_b200.habitat_eval import ConcurrentEvaluator
+    from streamvln_b200.tokenizer import StubQwenTokenizer
+
+    (tmp_path / "result.json").write_text("\n".join(l.decode() for l in gold["resume_prefill"].tolist()) + "\n")
+    tok = StubQwenTokenizer(152064)
+    model = fake_env.RecordingModel(tok, by_step=True)
+    args = SimpleNamespace(num_frames=32, num_future_steps=4, num_history=8, save_video=False, gpu_preprocess=False)
+    ev = ConcurrentEvaluator(3, config_path="config/vln_r2r.yaml", split="val_unseen", env_num=1, output_path=str(tmp_path), model=model,
+                             tokenizer=tok, epoch=0, args=args, env_factory=fake_env.FakeEnv, sim_sensors=fake_env.fake_sensors(),
+                             filter_depth=lambda d, blur_type=None: d, rank=0)
+    ret = ev.eval_action(0)
+    rows = [json.loads(l) for l in (tmp_path / "result.json").read_text().splitlines()]
+    done = [json.loads(l.decode())["episode_id"] for l in gold["resume_prefill"].tolist()]
+    assert int(ret[4]) == 7 and len(rows) == 7
+    assert sorted(r["episode_id"] for r in rows[3:]) == sorted({"1", "2", "3", "4", "5", "6", "7"} - set(done))
+    assert {c["views"][-1][1] for c in model.calls} == {int(e) for e in {"1", "2", "3", "4", "5", "6", "7"} - set(done)}

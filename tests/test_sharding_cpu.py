@@ -256,3 +256,13 @@ def test_run_episodes_refills_slots_and_keeps_the_cadence():
     # the hash is a pure function of the action list
     acts = [1 + (0 + k) % 3 for k in (1, 5, 9)]
     assert by[0].action_hash == hash_actions(acts)
+
+
+def test_attention_item_waits_for_its_tile_on_the_full_ring():
+    """attn_decode_body's FULL ring (the fused decode stack's 2-stage variant) refills a stage one iteration after it was
+    consumed, so the newest cp.async group IS the tile about to be read: the loop must wait for every group there
+    (`wait_group 1` let two-stream steps - splits of up to 4 tiles - read tiles still in flight; GPU regression test:
+    tests/test_gpu_7b_shape.py::test_decode_stack_is_deterministic_at_full_depth)."""
+    src = (Path(__file__).resolve().parent.parent / "streamvln_b200" / "csrc" / "attn_decode_body.cuh").read_text()
+    assert "cp_async_wait<FULL ? 0 : PRO - 1>();" in src
+    assert "cp_async_wait<PRO - 1>();" not in src
